@@ -1,0 +1,473 @@
+// scene.cpp -- scene.json loader, constructor-level scene creation, transforms, bounding boxes,
+// P3 PPM I/O. Host side of the drop-in boundary.
+//
+// Mirrors (same float operations, same order; compile with -ffp-contract=off):
+//   Camera::readCameraSpec        reference Code/camera.cpp:14-58
+//   parse_material                reference Code/json_loader.cpp:30-97
+//   load_lights_from_json         reference Code/json_loader.cpp:103-158
+//   load_shapes_from_json         reference Code/json_loader.cpp:164-338
+//   Shapes::buildTransformationMatrices  reference Code/shapes.cpp:92-139
+//   *::get_bounding_box           reference Code/shapes.cpp:264-287, 335-343, 425-433, 496-503
+//   Image::read / Image::write    reference Code/image.cpp:53-133
+#include "scene.hpp"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+#include <unordered_map>
+
+#include "json_min.hpp"
+
+namespace rtb {
+namespace {
+
+using jsonmin::Value;
+
+// ---- 4x4 helpers (shapes.cpp:92-149) ---------------------------------------------------------
+void mat_mul(const float A[4][4], const float B[4][4], float R[4][4]) {
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            float acc = 0.0f;
+            for (int k = 0; k < 4; ++k) acc += A[i][k] * B[k][j];
+            R[i][j] = acc;
+        }
+}
+
+void mat_set(float M[4][4], float a00, float a01, float a02, float a03, float a10, float a11, float a12, float a13,
+             float a20, float a21, float a22, float a23) {
+    float v[4][4] = {{a00, a01, a02, a03}, {a10, a11, a12, a13}, {a20, a21, a22, a23}, {0, 0, 0, 1}};
+    std::memcpy(M, v, sizeof(v));
+}
+
+// The reference calls the unqualified C functions cos()/sin() on floats (shapes.cpp:101-103);
+// with libstdc++ that resolves to the double overloads, and the result is narrowed to float.
+inline float cos_ref(float r) { return (float)::cos((double)r); }
+inline float sin_ref(float r) { return (float)::sin((double)r); }
+
+void build_transforms(const float t[3], const float r[3], const float s[3], HostPrim& p) {
+    float scale_m[4][4], rot_m[4][4], trans_m[4][4];
+    mat_set(scale_m, s[0], 0, 0, 0, 0, s[1], 0, 0, 0, 0, s[2], 0);
+    const float cx = cos_ref(r[0]), sx = sin_ref(r[0]);
+    const float cy = cos_ref(r[1]), sy = sin_ref(r[1]);
+    const float cz = cos_ref(r[2]), sz = sin_ref(r[2]);
+    mat_set(rot_m, cy * cz, sx * sy * cz - cx * sz, cx * sy * cz + sx * sz, 0,
+                   cy * sz, sx * sy * sz + cx * cz, cx * sy * sz - sx * cz, 0,
+                   -sy,     sx * cy,                cx * cy,                0);
+    mat_set(trans_m, 1, 0, 0, t[0], 0, 1, 0, t[1], 0, 0, 1, t[2]);
+    float rs[4][4];
+    mat_mul(rot_m, scale_m, rs);
+    mat_mul(trans_m, rs, p.o2w);
+
+    float inv_s[4][4], inv_r[4][4], inv_t[4][4];
+    mat_set(inv_s, 1.0f / s[0], 0, 0, 0, 0, 1.0f / s[1], 0, 0, 0, 0, 1.0f / s[2], 0);
+    mat_set(inv_r, rot_m[0][0], rot_m[1][0], rot_m[2][0], 0,
+                   rot_m[0][1], rot_m[1][1], rot_m[2][1], 0,
+                   rot_m[0][2], rot_m[1][2], rot_m[2][2], 0);
+    mat_set(inv_t, 1, 0, 0, -t[0], 0, 1, 0, -t[1], 0, 0, 1, -t[2]);
+    float sr[4][4];
+    mat_mul(inv_s, inv_r, sr);
+    mat_mul(sr, inv_t, p.w2o);
+}
+
+// transformPoint (shapes.cpp:151-158): the bottom row is (0,0,0,1) by construction, w == 1.
+void xform_point(const float m[4][4], const float p[3], float out[3]) {
+    const float w = m[3][0] * p[0] + m[3][1] * p[1] + m[3][2] * p[2] + m[3][3];
+    for (int i = 0; i < 3; ++i) out[i] = m[i][0] * p[0] + m[i][1] * p[1] + m[i][2] * p[2] + m[i][3];
+    if (std::fabs((double)(w - 1.0f)) > (double)1e-6f && w != 0) { out[0] /= w; out[1] /= w; out[2] /= w; }
+}
+
+void box_reset(Box& b) {
+    for (int i = 0; i < 3; ++i) { b.lo[i] = FLT_MAX; b.hi[i] = -FLT_MAX; }
+}
+void box_add(Box& b, const float p[3]) {
+    for (int i = 0; i < 3; ++i) { b.lo[i] = std::min(b.lo[i], p[i]); b.hi[i] = std::max(b.hi[i], p[i]); }
+}
+
+void compute_box(HostPrim& p) {
+    box_reset(p.box);
+    if (p.type == RT_SPHERE) {
+        static const float c[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1},
+                                      {-1, -1, 1},  {1, -1, 1},  {1, 1, 1},  {-1, 1, 1}};
+        for (int k = 0; k < 8; ++k) {
+            float w[3];
+            xform_point(p.o2w, c[k], w);
+            box_add(p.box, w);
+            float moved[3] = {w[0] + p.velocity[0], w[1] + p.velocity[1], w[2] + p.velocity[2]};
+            box_add(p.box, moved);
+        }
+    } else if (p.type == RT_CUBE) {
+        static const float c[8][3] = {{-0.5f, -0.5f, -0.5f}, {0.5f, -0.5f, -0.5f}, {0.5f, 0.5f, -0.5f}, {-0.5f, 0.5f, -0.5f},
+                                      {-0.5f, -0.5f, 0.5f},  {0.5f, -0.5f, 0.5f},  {0.5f, 0.5f, 0.5f},  {-0.5f, 0.5f, 0.5f}};
+        for (int k = 0; k < 8; ++k) { float w[3]; xform_point(p.o2w, c[k], w); box_add(p.box, w); }
+    } else if (p.type == RT_RECTANGLE) {
+        static const float c[4][3] = {{-0.5f, -0.5f, 0}, {0.5f, -0.5f, 0}, {0.5f, 0.5f, 0}, {-0.5f, 0.5f, 0}};
+        for (int k = 0; k < 4; ++k) { float w[3]; xform_point(p.o2w, c[k], w); box_add(p.box, w); }
+    } else {  // RT_PLANE, shapes.cpp:496-503
+        const float padding = 1e-4f;
+        for (int k = 0; k < 4; ++k) box_add(p.box, p.corners[k]);
+        for (int i = 0; i < 3; ++i) { p.box.lo[i] -= padding; p.box.hi[i] += padding; }
+    }
+}
+
+// Plane normal (shapes.cpp:446-451): cross(c1-c0, c2-c0), normalised; invalid if |n| < 1e-6.
+void compute_plane_normal(HostPrim& p) {
+    float e1[3], e2[3];
+    for (int i = 0; i < 3; ++i) { e1[i] = p.corners[1][i] - p.corners[0][i]; e2[i] = p.corners[2][i] - p.corners[0][i]; }
+    float n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+    const float len = (float)::sqrt((double)(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]));
+    p.normal_valid = !(len < 1e-6f);
+    for (int i = 0; i < 3; ++i) p.normal[i] = n[i] / len;
+}
+
+void identity(float M[4][4]) { mat_set(M, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0); }
+
+HostPrim make_prim(int type, int material, const float t[3], const float r[3], const float s[3], const float vel[3],
+                   const float* corners12) {
+    HostPrim p;
+    p.type = type;
+    p.material = material;
+    identity(p.w2o);
+    identity(p.o2w);
+    std::memset(p.corners, 0, sizeof(p.corners));
+    if (type == RT_PLANE) {
+        std::memcpy(p.corners, corners12, 12 * sizeof(float));
+        compute_plane_normal(p);
+    } else {
+        build_transforms(t, r, s, p);
+        if (type == RT_SPHERE) std::memcpy(p.velocity, vel, 3 * sizeof(float));
+    }
+    compute_box(p);
+    return p;
+}
+
+// ---- materials ------------------------------------------------------------------------------
+rt_material_desc default_material() {  // material.hpp:52-70
+    rt_material_desc m{};
+    m.diffuse_color[0] = m.diffuse_color[1] = m.diffuse_color[2] = 0.8f;
+    m.specular_color[0] = m.specular_color[1] = m.specular_color[2] = 1.0f;
+    m.k_ambient = 0.1f; m.k_diffuse = 0.9f; m.k_specular = 0.3f;
+    m.shininess = 20.0f; m.roughness = 0.0f;
+    m.reflectivity = 0.0f; m.transparency = 0.0f; m.refractive_index = 1.0f;
+    m.texture = -1;
+    return m;
+}
+
+struct MaterialTable {
+    std::vector<rt_material_desc>& out;
+    std::unordered_map<std::string, int> index;
+    explicit MaterialTable(std::vector<rt_material_desc>& o) : out(o) {}
+    int intern(const rt_material_desc& m) {
+        std::string key(reinterpret_cast<const char*>(&m), sizeof(m));
+        auto it = index.find(key);
+        if (it != index.end()) return it->second;
+        int id = (int)out.size();
+        out.push_back(m);
+        index.emplace(std::move(key), id);
+        return id;
+    }
+};
+
+struct TextureTable {
+    HostScene& scene;
+    std::string dir;
+    std::unordered_map<std::string, int> index;  // resolved path -> texture id or -1
+    int load(const std::string& texture_file) {
+        // json_loader.cpp:78-80: drop the 3-character extension, append "ppm".
+        if (texture_file.size() < 3) return -1;
+        std::string name = texture_file.substr(0, texture_file.size() - 3) + "ppm";
+        std::string path = dir + "/" + name;
+        auto it = index.find(path);
+        if (it != index.end()) return it->second;
+        Texture t;
+        int id = -1;
+        if (read_ppm_p3(path, t) && t.width != 0) {
+            id = (int)scene.textures.size();
+            scene.textures.push_back(std::move(t));
+        } else {
+            std::cerr << "Warning: Failed to load texture file: " << path << std::endl;
+        }
+        index.emplace(path, id);
+        return id;
+    }
+};
+
+rt_material_desc parse_material(const Value& mj, TextureTable& textures) {
+    rt_material_desc m = default_material();
+    try {
+        if (const Value* v = mj.find("diffuse_color")) v->as_float3(m.diffuse_color);
+        if (const Value* v = mj.find("specular_color")) v->as_float3(m.specular_color);
+        m.k_ambient = mj.value_float("k_ambient", 0.1f);
+        m.k_diffuse = mj.value_float("k_diffuse", 0.6f);
+        m.k_specular = mj.value_float("k_specular", 0.6f);
+        float roughness = mj.value_float("roughness", 0.001f);
+        roughness = std::max(0.001f, roughness);
+        const float r = std::max(0.001f, std::min(1.0f, roughness));
+        m.shininess = 5.0f / (r * r);
+        m.roughness = mj.value_float("roughness", 0.0f);
+        m.reflectivity = mj.value_float("reflectivity", 0.0f);
+        m.transparency = mj.value_float("transparency", 0.0f);
+        m.refractive_index = mj.value_float("refractive_index", 1.0f);
+        if (const Value* tf = mj.find("texture_file")) {
+            if (tf->is_string() && !tf->s.empty()) m.texture = textures.load(tf->s);
+        }
+    } catch (const std::exception& e) {
+        std::cerr << "Warning: Error parsing material data: " << e.what() << std::endl;
+        return default_material();
+    }
+    return m;
+}
+
+void load_camera(const Value& root, rt_camera_desc& c) {
+    // camera.cpp:26-48. Missing blocks are an error here (the reference prints and keeps zeros,
+    // which main() then rejects as "Camera resolution is 0", raytracer.cpp:403).
+    if (!root.contains("cameras") || !root.contains("render"))
+        throw std::runtime_error("JSON file is missing required keys (cameras, render)");
+    const Value& cams = root.at("cameras");
+    if (!cams.is_array() || cams.arr.empty()) throw std::runtime_error("'cameras' must be a non-empty array");
+    const Value& cj = cams.arr[0];
+    c.focal_length = cj.at("focal_length").as_float();
+    c.aperture = cj.value_float("aperture", 0.0f);
+    c.focus_dist = cj.value_float("focus_dist", 10.0f);
+    cj.at("location").as_float3(c.location);
+    cj.at("gaze_vector").as_float3(c.gaze);
+    cj.at("up_vector").as_float3(c.up);
+    c.sensor_width = cj.at("sensor_width").as_int();
+    c.sensor_height = cj.at("sensor_height").as_int();
+    c.res_x = root.at("render").at("resolution_x").as_int();
+    c.res_y = root.at("render").at("resolution_y").as_int();
+}
+
+void load_lights(const Value& root, std::vector<rt_light_desc>& lights) {
+    const Value* lj = root.find("lights");
+    if (!lj) { std::cerr << "Warning: No valid lights were loaded." << std::endl; return; }
+    if (!lj->is_array()) { std::cerr << "Warning: 'lights' key found but is not an array. No lights loaded." << std::endl; return; }
+    for (const Value& l : lj->arr) {
+        if (!l.is_object()) { std::cerr << "Warning: Skipping non-object entry in 'lights' array." << std::endl; continue; }
+        try {
+            if (!l.contains("location") || !l.contains("color") || !l.contains("intensity")) {
+                std::cerr << "Warning: Skipping invalid light definition." << std::endl;
+                continue;
+            }
+            rt_light_desc d{};
+            l.at("location").as_float3(d.location);
+            l.at("color").as_float3(d.color);
+            d.intensity = l.at("intensity").as_float();
+            d.radius = l.value_float("radius", 0.0f);
+            if (d.intensity <= 0) { std::cerr << "Warning: Skipping light with non-positive intensity." << std::endl; continue; }
+            lights.push_back(d);
+        } catch (const std::exception& e) {
+            std::cerr << "Warning: Error parsing light entry: " << e.what() << std::endl;
+        }
+    }
+    if (lights.empty()) std::cerr << "Warning: No valid lights were loaded." << std::endl;
+}
+
+void load_shapes(const Value& root, HostScene& s, MaterialTable& mats, TextureTable& textures) {
+    const float zero3[3] = {0, 0, 0};
+    auto material_of = [&](const Value& j) {
+        rt_material_desc m = default_material();
+        if (const Value* mj = j.find("material")) m = parse_material(*mj, textures);
+        return mats.intern(m);
+    };
+    // 1. spheres (json_loader.cpp:180-234)
+    if (const Value* arr = root.find("spheres"); arr && arr->is_array()) {
+        for (const Value& j : arr->arr) {
+            if (!j.is_object()) continue;
+            try {
+                float t[3], r[3] = {0, 0, 0}, sc[3] = {1, 1, 1}, vel[3] = {0, 0, 0};
+                j.at("location").as_float3(t);
+                if (const Value* v = j.find("rotation")) v->as_float3(r);
+                const Value* sv = j.find("scale");
+                if (sv && sv->is_array()) sv->as_float3(sc);
+                else if (const Value* rv = j.find("radius")) { float rad = rv->as_float(); sc[0] = sc[1] = sc[2] = rad; }
+                int mat = material_of(j);
+                if (const Value* v = j.find("velocity")) v->as_float3(vel);
+                vel[0] = vel[0] / 5; vel[1] = vel[1] / 5; vel[2] = vel[2] / 5;
+                s.prims.push_back(make_prim(RT_SPHERE, mat, t, r, sc, vel, nullptr));
+            } catch (const std::exception& e) {
+                std::cerr << "Warning: Error parsing sphere: " << e.what() << std::endl;
+            }
+        }
+    }
+    // 2. cubes (json_loader.cpp:237-278)
+    if (const Value* arr = root.find("cubes"); arr && arr->is_array()) {
+        for (const Value& j : arr->arr) {
+            if (!j.is_object()) continue;
+            try {
+                if (!j.contains("translation") || !j.contains("rotation")) {
+                    std::cerr << "Warning: Skipping invalid cube definition." << std::endl;
+                    continue;
+                }
+                float t[3], r[3], sc[3] = {1, 1, 1};
+                j.at("translation").as_float3(t);
+                j.at("rotation").as_float3(r);
+                if (const Value* sv = j.find("scale")) {
+                    if (sv->is_array()) sv->as_float3(sc);
+                    else if (sv->is_number()) { float v = sv->as_float(); sc[0] = sc[1] = sc[2] = v; }
+                }
+                int mat = material_of(j);
+                s.prims.push_back(make_prim(RT_CUBE, mat, t, r, sc, zero3, nullptr));
+            } catch (const std::exception& e) {
+                std::cerr << "Warning: Error parsing cube entry: " << e.what() << std::endl;
+            }
+        }
+    }
+    // 3. rectangles (json_loader.cpp:282-301)
+    if (const Value* arr = root.find("rectangles"); arr && arr->is_array()) {
+        for (const Value& j : arr->arr) {
+            if (!j.is_object()) continue;
+            try {
+                float t[3], r[3], sc[3];
+                j.at("translation").as_float3(t);
+                j.at("rotation").as_float3(r);
+                j.at("scale").as_float3(sc);
+                int mat = material_of(j);
+                s.prims.push_back(make_prim(RT_RECTANGLE, mat, t, r, sc, zero3, nullptr));
+            } catch (const std::exception& e) {
+                std::cerr << "Warning: Error parsing rectangle: " << e.what() << std::endl;
+            }
+        }
+    }
+    // 4. planes (json_loader.cpp:304-332)
+    if (const Value* arr = root.find("planes"); arr && arr->is_array()) {
+        for (const Value& j : arr->arr) {
+            if (!j.is_object()) continue;
+            try {
+                const Value* cj = j.find("corners");
+                if (!cj || !cj->is_array() || cj->arr.size() != 4) {
+                    std::cerr << "Warning: Skipping invalid plane definition." << std::endl;
+                    continue;
+                }
+                float corners[12];
+                for (int k = 0; k < 4; ++k) cj->arr[k].as_float3(corners + 3 * k);
+                int mat = material_of(j);
+                s.prims.push_back(make_prim(RT_PLANE, mat, zero3, zero3, zero3, zero3, corners));
+            } catch (const std::exception& e) {
+                std::cerr << "Warning: Error parsing plane entry: " << e.what() << std::endl;
+            }
+        }
+    }
+    if (s.prims.empty()) std::cerr << "Warning: No valid shapes were loaded." << std::endl;
+}
+
+void normalize3(const float v[3], float out[3]) {  // camera.cpp:60-68
+    const float mag = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (mag == 0.0f) { out[0] = out[1] = out[2] = 0.0f; return; }
+    out[0] = v[0] / mag; out[1] = v[1] / mag; out[2] = v[2] / mag;
+}
+void cross3(const float a[3], const float b[3], float out[3]) {  // camera.cpp:70-87
+    const float x = a[1] * b[2] - a[2] * b[1];
+    const float y = a[2] * b[0] - a[0] * b[2];
+    const float z = a[0] * b[1] - a[1] * b[0];
+    out[0] = x; out[1] = y; out[2] = z;
+}
+
+}  // namespace
+
+void finalize_scene(HostScene& s) {
+    // Camera basis (camera.cpp:109-115); the reference recomputes it for every ray with the same
+    // operands, so computing it once gives the same bits.
+    float tmp[3];
+    normalize3(s.cam.gaze, s.zdir);
+    cross3(s.cam.up, s.zdir, tmp);
+    normalize3(tmp, s.xdir);
+    cross3(s.zdir, s.xdir, tmp);
+    normalize3(tmp, s.ydir);
+    build_bvh(s);
+    flatten_scene(s);
+}
+
+void load_scene_json(const std::string& path, const std::string& texture_dir, HostScene& s) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f.is_open()) throw std::runtime_error("Could not open JSON file: " + path);
+    std::stringstream buf;
+    buf << f.rdbuf();
+    const std::string text = buf.str();
+    Value root = jsonmin::parse(text);
+    if (!root.is_object()) throw std::runtime_error("scene root must be a JSON object");
+    load_camera(root, s.cam);
+    load_lights(root, s.lights);
+    MaterialTable mats(s.materials);
+    TextureTable textures{s, texture_dir.empty() ? std::string("../../Textures") : texture_dir, {}};
+    load_shapes(root, s, mats, textures);
+    finalize_scene(s);
+}
+
+void create_scene_from_desc(const rt_scene_desc& d, HostScene& s) {
+    s.cam = d.camera;
+    s.lights.assign(d.lights, d.lights + d.n_lights);
+    s.materials.assign(d.materials, d.materials + d.n_materials);
+    for (int i = 0; i < d.n_textures; ++i) {
+        Texture t;
+        t.width = d.textures[i].width;
+        t.height = d.textures[i].height;
+        t.rgb.assign(d.textures[i].rgb, d.textures[i].rgb + (size_t)t.width * t.height * 3);
+        s.textures.push_back(std::move(t));
+    }
+    if (s.materials.empty()) s.materials.push_back(default_material());
+    for (const rt_material_desc& m : s.materials)
+        if (m.texture >= d.n_textures) throw std::runtime_error("material references a texture that does not exist");
+    s.prims.reserve(d.n_shapes);
+    for (int i = 0; i < d.n_shapes; ++i) {
+        const rt_shape_desc& sh = d.shapes[i];
+        if (sh.type < RT_SPHERE || sh.type > RT_PLANE) throw std::runtime_error("unknown shape type");
+        if (sh.material < 0 || sh.material >= (int)s.materials.size()) throw std::runtime_error("shape material out of range");
+        s.prims.push_back(make_prim(sh.type, sh.material, sh.translation, sh.rotation, sh.scale, sh.velocity, sh.corners));
+    }
+    finalize_scene(s);
+}
+
+// ---- P3 PPM (image.cpp:53-133) ----------------------------------------------------------------
+bool read_ppm_p3(const std::string& path, Texture& out) {
+    std::ifstream file(path);
+    if (!file.is_open()) { std::cerr << "Error: Could not open file " << path << " for reading\n"; return false; }
+    std::string magic, line;
+    file >> magic;
+    if (magic != "P3") { std::cerr << "Error: Only P3 PPM format is supported\n"; return false; }
+    file >> std::ws;
+    while (file.peek() == '#') { std::getline(file, line); file >> std::ws; }
+    int w = 0, h = 0, maxc = 0;
+    file >> w >> h >> maxc;
+    if (w <= 0 || h <= 0) return false;
+    if (maxc != 255) std::cerr << "Warning: Max color value is " << maxc << ", expected 255\n";
+    out.width = w;
+    out.height = h;
+    out.rgb.resize((size_t)w * h * 3);
+    for (size_t i = 0; i < out.rgb.size(); ++i) {
+        int v = 0;
+        file >> v;
+        out.rgb[i] = (uint8_t)std::max(0, std::min(v, 255));
+    }
+    return true;
+}
+
+bool write_ppm_p3(const std::string& path, int width, int height, const uint8_t* rgb) {
+    FILE* f = std::fopen(path.c_str(), "w");
+    if (!f) { std::cerr << "Error: Could not open file " << path << " for writing\n"; return false; }
+    // Same byte stream as Image::write: "P3\nW H\n255\n", pixels as "r g b" joined by two spaces.
+    std::string buf;
+    buf.reserve((size_t)width * 14 + 16);
+    std::fprintf(f, "P3\n%d %d\n255\n", width, height);
+    char tmp[16];
+    for (int y = 0; y < height; ++y) {
+        buf.clear();
+        for (int x = 0; x < width; ++x) {
+            const uint8_t* p = rgb + ((size_t)y * width + x) * 3;
+            int n = std::snprintf(tmp, sizeof(tmp), "%d %d %d", (int)p[0], (int)p[1], (int)p[2]);
+            buf.append(tmp, (size_t)n);
+            if (x < width - 1) buf.append("  ");
+        }
+        buf.push_back('\n');
+        std::fwrite(buf.data(), 1, buf.size(), f);
+    }
+    std::fclose(f);
+    return true;
+}
+
+}  // namespace rtb
