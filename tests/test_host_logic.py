@@ -1,0 +1,179 @@
+"""CPU tests of the host side of the drop-in boundary: the C ABI loads and exports every symbol
+include/rt_render.h declares, the C++ scene loader agrees with an independent Python restatement
+of the reference loader, the BVH equals the reference's tree, PPM I/O, argument checking, and the
+'no GPU -> fail loudly' rule. No compute calls are made here."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, golden_data, golden_scene, scene_file, with_resolution
+
+
+def test_library_exports_every_declared_symbol(rt):
+    header = open(os.path.join(ROOT, "include", "rt_render.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(rt_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 18
+    lib = C.CDLL(os.path.join(ROOT, "ray_tracying_b200", "librt_b200.so"))
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"librt_b200.so does not export {name}"
+    from ray_tracying_b200 import _lib
+    assert declared == set(_lib.SYMBOLS), "python binding and header disagree"
+
+
+def test_struct_sizes_match_header(rt):
+    from ray_tracying_b200 import _lib
+    assert C.sizeof(_lib.CameraDesc) == 4 * (9 + 1 + 2 + 2 + 2)
+    assert C.sizeof(_lib.LightDesc) == 32
+    assert C.sizeof(_lib.MaterialDesc) == 60
+    assert C.sizeof(_lib.ShapeDesc) == 104
+    assert C.sizeof(_lib.RenderParams) == 80
+    assert C.sizeof(_lib.RenderStats) == 64
+
+
+def test_defaults_are_the_reference_cli_defaults(rt):
+    p = rt.make_params()
+    # raytracer.cpp:361-363 and raytracer.hpp:11
+    assert (p.use_bvh, p.samples_sqrt, p.light_samples, p.max_depth) == (0, 4, 1, 10)
+    assert (p.rank, p.world) == (0, 1)
+
+
+@pytest.mark.parametrize("name", ["mixed_400", "few_3", "few_5", "ties_axis_aligned", "textured_40", "empty"])
+def test_bvh_equals_reference_tree(rt, name):
+    """Tree topology, leaf contents and every box bit-equal to the reference's (golden dump)."""
+    scene = rt.Scene.from_json(os.path.join(GOLDEN, name + ".json"), GOLDEN)
+    ref = json.loads(str(golden_data(name)["bvh_dump"]))
+    mine = scene.dump_bvh()
+    assert len(mine) == len(ref)
+    for a, b in zip(mine, ref):
+        assert a[0] == b[0] and a[3] == b[3]
+        assert np.array_equal(np.float32(a[1]), np.float32(b[1])) and np.array_equal(np.float32(a[2]), np.float32(b[2]))
+
+
+def test_ascii_scene_counts_and_tree(rt, tmp_path):
+    scene = rt.Scene.from_json(os.path.join(GOLDEN, "ascii_scene.json"), GOLDEN)
+    assert scene.resolution == (1920, 1080)
+    c = scene.counts()
+    assert c["shapes"] == 141 and c["lights"] == 2 and c["materials"] == 1
+    ref = json.loads(str(golden_data("ascii_scene_480")["bvh_dump"]))
+    assert [(n[0], n[3]) for n in scene.dump_bvh()] == [(n[0], n[3]) for n in ref]
+
+
+def test_loader_matches_python_restatement(rt, oracle_mod, tmp_path):
+    """C++ JSON path (rt_scene_load_json) and the array path fed by oracle/scene_io.py build the same scene."""
+    from oracle import scene_io
+    d = golden_scene("textured_40")
+    cam, lights, mats, shapes, tex = scene_io.scene_arrays(d, GOLDEN)
+    a = rt.Scene.from_json(os.path.join(GOLDEN, "textured_40.json"), GOLDEN)
+    mats15 = np.concatenate([mats["f"], mats["texture"].astype(np.float32)[:, None]], axis=1)
+    b = rt.Scene.from_arrays(cam, lights.view(np.float32).reshape(-1, 8), mats15, shapes.view(rt.SHAPE_DTYPE), tex)
+    assert a.counts() == b.counts()
+    assert np.array_equal(a.shape_order(), b.shape_order())
+    assert a.dump_bvh() == b.dump_bvh()
+    o = oracle_mod.OracleScene(cam, lights, mats, shapes, tex)
+    assert np.array_equal(o.shape_order(), a.shape_order())
+
+
+def test_sensor_size_is_truncated_like_the_reference(rt, tmp_path):
+    # camera.cpp:39-40 reads sensor_width/height with get<int>()
+    d = golden_scene("few_3")
+    d["cameras"][0]["sensor_width"] = 36.9
+    p = scene_file(tmp_path, d)
+    from oracle import scene_io
+    cam = scene_io.load_scene(p, GOLDEN)[0]
+    assert cam["sensor_width"] == 36
+    rt.Scene.from_json(p, GOLDEN)
+
+
+def test_invalid_entries_are_skipped_like_the_reference(rt, tmp_path):
+    d = golden_scene("few_3")
+    n0 = rt.Scene.from_json(scene_file(tmp_path, d), GOLDEN).counts()
+    d["cubes"] = d.get("cubes", []) + [{"rotation": [0, 0, 0]}, 7]           # no translation / not an object
+    d["planes"] = d.get("planes", []) + [{"corners": [[0, 0, 0]]}]            # not 4 corners
+    d["lights"] = d["lights"] + [{"location": [0, 0, 1], "color": [1, 1, 1], "intensity": 0.0}, {"color": [1, 1, 1]}]
+    n1 = rt.Scene.from_json(scene_file(tmp_path, d, "b.json"), GOLDEN).counts()
+    assert n1["shapes"] == n0["shapes"] and n1["lights"] == n0["lights"]
+
+
+def test_missing_file_and_bad_json_report_errors(rt, tmp_path):
+    with pytest.raises(rt.RtError) as e:
+        rt.Scene.from_json(str(tmp_path / "nope.json"))
+    assert e.value.status == -2
+    bad = tmp_path / "bad.json"
+    bad.write_text("{\"cameras\": [")
+    with pytest.raises(rt.RtError):
+        rt.Scene.from_json(str(bad))
+    nocam = tmp_path / "nocam.json"
+    nocam.write_text("{\"lights\": []}")
+    with pytest.raises(rt.RtError):
+        rt.Scene.from_json(str(nocam))
+
+
+def test_ppm_roundtrip_and_reference_format(rt, tmp_path):
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (5, 7, 3), dtype=np.uint8)
+    p = str(tmp_path / "a.ppm")
+    rt.write_ppm(p, img)
+    text = open(p).read().splitlines()
+    assert text[0] == "P3" and text[1] == "7 5" and text[2] == "255"
+    # Image::write separates pixels by two spaces and channels by one (image.cpp:66-78)
+    assert text[3] == "  ".join(" ".join(str(int(v)) for v in px) for px in img[0])
+    assert np.array_equal(rt.read_ppm(p), img)
+    tex = rt.read_ppm(os.path.join(GOLDEN, "checker.ppm"))
+    assert tex.shape == (32, 32, 3)
+
+
+def test_shard_pixels_partition_the_frame(rt):
+    scene = rt.Scene.from_json(os.path.join(GOLDEN, "mixed_400.json"), GOLDEN)
+    w, h = scene.resolution
+    from ray_tracying_b200 import dist
+    for world in (1, 2, 3, 8):
+        for tile in ((32, 32), (64, 16), (8, 4)):
+            counts = [scene.shard_pixels(rt.make_params(rank=r, world=world, tile=tile)) for r in range(world)]
+            assert sum(counts) == w * h
+            owner = dist.tile_owner(w, h, tile, world)
+            assert counts == [int((owner == r).sum()) for r in range(world)]
+
+
+def test_bad_params_are_rejected(rt):
+    scene = rt.Scene.from_json(os.path.join(GOLDEN, "few_3.json"), GOLDEN)
+    for kw in (dict(rank=2, world=2), dict(tile=(30, 32)), dict(tile=(32, 6))):
+        with pytest.raises(rt.RtError) as e:
+            scene.shard_pixels(rt.make_params(**kw))
+        assert e.value.status == -1
+
+
+def test_render_without_gpu_fails_loudly(rt):
+    if rt.device_count() > 0:
+        pytest.skip("a GPU is present")
+    scene = rt.Scene.from_json(os.path.join(GOLDEN, "few_3.json"), GOLDEN)
+    with pytest.raises(rt.RtError) as e:
+        scene.render(use_bvh=True, n_samples_sqrt=1)
+    assert e.value.status == -3 and "no CPU fallback" in str(e.value)
+    with pytest.raises(rt.RtError):
+        scene.upload()
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "ray_tracying_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".hpp", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "rt_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_cli_usage_error_matches_reference(rt):
+    exe = os.path.join(ROOT, "ray_tracying_b200", "bin", "Raytracer")
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1
+    assert "Please specify scene file name" in r.stderr  # raytracer.cpp:392
+    if rt.device_count() == 0:
+        r = subprocess.run([exe, "-input", os.path.join(GOLDEN, "few_3.json"), "-output", "/tmp/x.ppm", "-bvh", "-s", "1"],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr

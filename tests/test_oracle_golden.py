@@ -1,0 +1,145 @@
+"""CPU tests that PIN THE ORACLE: oracle/rt_oracle.cpp against golden vectors produced by the
+unmodified reference (tests/golden/make_golden.py), and -- when oracle/_ref/ref_driver is present
+-- against the reference itself on fresh random scenes.
+
+Bar: bit-exact hit IDs, hit distances and linear float colour for deterministic scenes (both are
+x86-64 builds using the same libm); RMSE <= 1e-2 against the reference's 4096-spp render for
+stochastic effects (the oracle draws from the reference's distributions with a different RNG)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_data, golden_scene, rmse, scene_file, with_resolution
+
+DETERMINISTIC = ["mixed_400", "mixed_400_depth5", "few_3", "few_5", "ties_axis_aligned", "textured_40", "empty"]
+STOCHASTIC = ["soft_shadows", "glossy", "dof", "motion_blur", "antialias"]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def test_philox_known_answers(oracle_mod):
+    # Random123 known-answer vectors for Philox4x32-10
+    kat = [
+        ([0, 0, 0, 0], [0, 0], [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+        ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+        ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0], [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]),
+    ]
+    for ctr, key, want in kat:
+        assert list(oracle_mod.philox4x32_10(ctr, key)) == want
+
+
+@pytest.mark.parametrize("name", DETERMINISTIC)
+@pytest.mark.parametrize("use_bvh", [True, False])
+def test_oracle_matches_reference_golden(oracle_mod, name, use_bvh):
+    g = golden_data(name)
+    o = oracle_mod.OracleScene.from_dict(golden_scene(name), GOLDEN)
+    r = o.render(use_bvh=use_bvh, n_samples_sqrt=1, fixed_time=0.0, max_depth=int(g["depth"]))
+    k = f"bvh{int(use_bvh)}"
+    assert np.array_equal(r["ids"], g["ids_" + k])
+    assert np.array_equal(bits(r["t"]), bits(g["t_" + k]))
+    assert np.array_equal(bits(r["linear"]), bits(g["linear_" + k]))
+    assert np.array_equal(r["rgb"], g["rgb_" + k])
+
+
+@pytest.mark.parametrize("name", DETERMINISTIC)
+def test_oracle_tree_equals_reference_tree(oracle_mod, name):
+    o = oracle_mod.OracleScene.from_dict(golden_scene(name), GOLDEN)
+    ref = json.loads(str(golden_data(name)["bvh_dump"]))
+    mine = o.dump_bvh()
+    assert len(mine) == len(ref)
+    for a, b in zip(mine, ref):
+        assert a[0] == b[0] and a[3] == b[3]
+        assert np.array_equal(np.float32(a[1]), np.float32(b[1])) and np.array_equal(np.float32(a[2]), np.float32(b[2]))
+
+
+def test_oracle_on_the_references_own_scene(oracle_mod):
+    """ASCII/scene.json (config 0) at 480x270: primary hit IDs and distances, tree and linear scan."""
+    g = golden_data("ascii_scene_480")
+    o = oracle_mod.OracleScene.from_dict(with_resolution(golden_scene("ascii_scene"), 480, 270), GOLDEN)
+    for use_bvh in (True, False):
+        r = o.render(use_bvh=use_bvh, n_samples_sqrt=1, fixed_time=0.0, max_depth=0)
+        k = f"bvh{int(use_bvh)}"
+        assert np.array_equal(r["ids"], g["ids_" + k])
+        assert np.array_equal(bits(r["t"]), bits(g["t_" + k]))
+
+
+def test_tie_breaking_first_in_leaf_order(oracle_mod):
+    """Coincident shapes: the reference keeps the FIRST minimum (std::min_element / strict <)."""
+    g = golden_data("ties_axis_aligned")
+    ids = g["ids_bvh1"]
+    assert (ids >= 0).any()
+    o = oracle_mod.OracleScene.from_dict(golden_scene("ties_axis_aligned"), GOLDEN)
+    order = list(o.shape_order())
+    pos = {s: i for i, s in enumerate(order)}
+    # load order: spheres 0,1 ; cubes 2,3,4 ; rectangle 5 (floor) ; planes 6..9
+    for a, b in ((0, 1), (2, 3), (6, 7)):
+        seen = set(np.unique(ids)) & {a, b}
+        assert len(seen) == 1, "exactly one of two coincident shapes may ever be reported"
+        assert seen.pop() == (a if pos[a] < pos[b] else b)
+    assert 8 not in ids  # the degenerate plane never hits (shapes.cpp:450)
+
+
+@pytest.mark.parametrize("name", STOCHASTIC)
+def test_oracle_stochastic_effects_converge_to_reference(oracle_mod, name):
+    g = golden_data(name)
+    o = oracle_mod.OracleScene.from_dict(golden_scene(name), GOLDEN)
+    r = o.render(use_bvh=True, n_samples_sqrt=32, light_samples=int(g["light_samples"]), max_depth=int(g["depth"]), seed=11)
+    err = rmse(r["linear"], g["ref_linear"])
+    assert err <= 1e-2, f"{name}: RMSE {err:.4f} against the reference's {int(g['ref_spp'])}-spp render"
+
+
+def test_oracle_ascii_scene_glossy_converges(oracle_mod):
+    g = golden_data("ascii_scene_96")
+    o = oracle_mod.OracleScene.from_dict(with_resolution(golden_scene("ascii_scene"), 96, 54), GOLDEN)
+    r = o.render(use_bvh=True, n_samples_sqrt=32, seed=3)
+    assert rmse(r["linear"], g["ref_linear"]) <= 1e-2
+
+
+def test_oracle_is_independent_of_thread_count_and_rows(oracle_mod):
+    o = oracle_mod.OracleScene.from_dict(golden_scene("glossy"), GOLDEN)
+    a = o.render(use_bvh=True, n_samples_sqrt=2, threads=1)
+    b = o.render(use_bvh=True, n_samples_sqrt=2, threads=5)
+    assert np.array_equal(bits(a["linear"]), bits(b["linear"])) and a["rays"] == b["rays"]
+    c = o.render(use_bvh=True, n_samples_sqrt=2, rows=(10, 20))
+    assert np.array_equal(bits(c["linear"][10:20]), bits(a["linear"][10:20]))
+
+
+# ---- live comparison with the compiled reference (this container; skipped where it is absent) ---
+def _ref(oracle_mod):
+    if not oracle_mod.RefDriver.available():
+        pytest.skip("oracle/_ref/ref_driver not built (no /root/reference here)")
+    return oracle_mod.RefDriver
+
+
+@pytest.mark.parametrize("seed", [101, 102, 103])
+def test_oracle_vs_live_reference_random_scenes(oracle_mod, tmp_path, seed):
+    ref = _ref(oracle_mod)
+    from ray_tracying_b200 import scenes
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(6, 300))
+    sc = scenes.mixed_scene(n, seed=seed, resolution=(120, 68), extent=float(rng.uniform(2, 12)), height=float(rng.uniform(1, 5)))
+    p = scene_file(tmp_path, sc)
+    o = oracle_mod.OracleScene.from_dict(sc, GOLDEN)
+    assert ref.bvh(p) == o.dump_bvh()
+    for use_bvh in (True, False):
+        ids, t, _ = ref.ids(p, use_bvh=use_bvh)
+        _, lin, _ = ref.render(p, use_bvh=use_bvh, n_samples_sqrt=1, max_depth=6)
+        r = o.render(use_bvh=use_bvh, n_samples_sqrt=1, fixed_time=0.0, max_depth=6)
+        assert np.array_equal(r["ids"], ids)
+        assert np.array_equal(bits(r["t"]), bits(t))
+        assert np.array_equal(bits(r["linear"]), bits(lin))
+
+
+def test_live_reference_depth_entry_trick(oracle_mod, tmp_path):
+    """ref_driver --depth D enters Trace() at depth 10-D; D=10 must equal the stock recursion."""
+    ref = _ref(oracle_mod)
+    p = os.path.join(GOLDEN, "mixed_400_depth5.json")
+    g10 = golden_data("mixed_400")  # same scene at 320x180, depth 10
+    _, lin5, _ = ref.render(p, use_bvh=True, n_samples_sqrt=1, max_depth=5)
+    assert np.array_equal(bits(lin5), bits(golden_data("mixed_400_depth5")["linear_bvh1"]))
+    _, lin10, _ = ref.render(os.path.join(GOLDEN, "mixed_400.json"), use_bvh=True, n_samples_sqrt=1, max_depth=10)
+    assert np.array_equal(bits(lin10), bits(g10["linear_bvh1"]))
