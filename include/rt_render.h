@@ -171,7 +171,13 @@ int rt_scene_upload(rt_scene* scene, uint64_t* bytes);
 /* Drops the device copy so that the next render uploads again (end-to-end timing). */
 int rt_scene_evict(rt_scene* scene);
 
-/* Number of pixels and the byte size of the compact per-rank output for (rank, world, tile). */
+/* CUDA-event timings of the most recent rt_render_device / rt_render call on this scene: the
+ * render kernels alone, and everything the call put on the stream. The events are recorded on
+ * the launching stream by every call; this getter waits for them, so it can be used after an
+ * asynchronous rt_render_device(stats = NULL) without perturbing the timed region. */
+int rt_scene_last_timing(rt_scene* scene, float* kernel_ms, float* total_ms);
+
+/* Number of pixels this rank renders for (rank, world, tile). */
 int rt_shard_pixels(const rt_scene* scene, const rt_render_params* p, int64_t* n_pixels);
 
 /* Replaces the frame loop raytracer.cpp:433-476 for this rank's tiles. Device-resident outputs,

@@ -44,12 +44,13 @@ struct Options {
     unsigned seed = 1;
     int row0 = 0, row1 = -1;
     float fixed_time = -1.0f;  // ids mode: ray.time; <0 -> 0
+    int repeat = 1;            // render mode: render the band this many times, report each time
 };
 
 void usage() {
     std::fprintf(stderr,
         "ref_driver --scene F [--mode render|ids|bvh] [--bvh 0|1] [--s N] [--light-samples N]\n"
-        "           [--depth D] [--seed S] [--rows Y0 Y1] [--time T]\n"
+        "           [--depth D] [--seed S] [--rows Y0 Y1] [--time T] [--repeat N]\n"
         "           [--out-ppm F] [--out-raw F] [--out-ids F] [--out-bvh F]\n");
 }
 
@@ -69,6 +70,7 @@ bool parse(int argc, char** argv, Options& o) {
         else if (a == "--seed") o.seed = (unsigned)std::strtoul(next("--seed"), nullptr, 10);
         else if (a == "--rows") { o.row0 = std::atoi(next("--rows")); o.row1 = std::atoi(next("--rows")); }
         else if (a == "--time") o.fixed_time = (float)std::atof(next("--time"));
+        else if (a == "--repeat") o.repeat = std::max(1, std::atoi(next("--repeat")));
         else if (a == "--out-ppm") o.out_ppm = next("--out-ppm");
         else if (a == "--out-raw") o.out_raw = next("--out-raw");
         else if (a == "--out-ids") o.out_ids = next("--out-ids");
@@ -172,6 +174,9 @@ int main(int argc, char** argv) {
         const int rows = row1 - row0;
         std::vector<unsigned char> rgb((size_t)width * rows * 3);
         std::vector<float> raw((size_t)width * rows * 3);
+        std::vector<double> times;
+        for (int rep = 0; rep < opt.repeat; ++rep) {
+        gen.seed(opt.seed);
         auto t0 = std::chrono::steady_clock::now();
         for (int y = row0; y < row1; ++y) {
             for (int x = 0; x < width; ++x) {
@@ -204,7 +209,9 @@ int main(int argc, char** argv) {
             }
         }
         auto t1 = std::chrono::steady_clock::now();
-        const double secs = std::chrono::duration<double>(t1 - t0).count();
+        times.push_back(std::chrono::duration<double>(t1 - t0).count());
+        }  // repeat
+        const double secs = times.back();
 
         if (!opt.out_ppm.empty()) {
             Image img(width, rows);
@@ -224,8 +231,10 @@ int main(int argc, char** argv) {
             std::fwrite(raw.data(), sizeof(float), raw.size(), f);
             std::fclose(f);
         }
-        std::printf("{\"mode\":\"render\",\"width\":%d,\"rows\":%d,\"spp\":%d,\"seconds\":%.6f,\"build_seconds\":%.6f}\n",
-                    width, rows, opt.s <= 1 ? 1 : opt.s * opt.s, secs, build_s);
+        std::string all;
+        for (size_t i = 0; i < times.size(); ++i) { char b[32]; std::snprintf(b, sizeof(b), "%s%.6f", i ? "," : "", times[i]); all += b; }
+        std::printf("{\"mode\":\"render\",\"width\":%d,\"rows\":%d,\"spp\":%d,\"seconds\":%.6f,\"all_seconds\":[%s],\"build_seconds\":%.6f}\n",
+                    width, rows, opt.s <= 1 ? 1 : opt.s * opt.s, secs, all.c_str(), build_s);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "ref_driver: %s\n", e.what());
         return 1;

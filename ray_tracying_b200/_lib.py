@@ -100,6 +100,7 @@ SYMBOLS = {
     "rt_scene_dump_bvh": (C.c_int, [_VP, C.POINTER(BvhNodeDump), C.c_int32]),
     "rt_scene_upload": (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
     "rt_scene_evict": (C.c_int, [_VP]),
+    "rt_scene_last_timing": (C.c_int, [_VP, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "rt_shard_pixels": (C.c_int, [_VP, C.POINTER(RenderParams), C.POINTER(C.c_int64)]),
     "rt_render_device": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _VP, _VP, _VP, C.POINTER(RenderStats)]),
     "rt_render": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _VP, _VP, C.POINTER(RenderStats)]),

@@ -170,6 +170,12 @@ class Scene:
     def evict(self) -> None:
         check(lib.rt_scene_evict(self._h), "rt_scene_evict")
 
+    def last_timing(self) -> tuple[float, float]:
+        """(kernel_ms, total_ms) of the most recent render call, from CUDA events on its stream."""
+        k, t = C.c_float(), C.c_float()
+        check(lib.rt_scene_last_timing(self._h, C.byref(k), C.byref(t)), "rt_scene_last_timing")
+        return k.value, t.value
+
     def shard_pixels(self, params: RenderParams) -> int:
         n = C.c_int64()
         check(lib.rt_shard_pixels(self._h, C.byref(params), C.byref(n)), "rt_shard_pixels")

@@ -806,6 +806,8 @@ struct DeviceScene {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int blocks_per_sm[2] = {0, 0};
     int sm_count = 0;
+    bool timed = false;               // ev[0..2] have been recorded at least once
+    std::vector<void*> pinned;        // host ranges registered for fast H2D staging
 };
 
 #define CUDA_TRY(expr)                                                                         \
@@ -818,11 +820,18 @@ struct DeviceScene {
     } while (0)
 
 template <typename T>
-static int upload_vec(const std::vector<T>& v, void** dst, uint64_t& bytes) {
+static int upload_vec(const std::vector<T>& v, void** dst, uint64_t& bytes, DeviceScene* d) {
     *dst = nullptr;
     const size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
     CUDA_TRY(cudaMalloc(dst, n));
     if (!v.empty()) {
+        // page-lock large host arrays so the copy runs at full PCIe rate (best effort)
+        if (v.size() * sizeof(T) >= (1u << 20)) {
+            if (cudaHostRegister((void*)v.data(), v.size() * sizeof(T), cudaHostRegisterDefault) == cudaSuccess)
+                d->pinned.push_back((void*)v.data());
+            else
+                cudaGetLastError();
+        }
         CUDA_TRY(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
         bytes += v.size() * sizeof(T);
     }
@@ -834,6 +843,7 @@ static void free_device(DeviceScene* d) {
     cudaFree(d->prims); cudaFree(d->nodes); cudaFree(d->mats); cudaFree(d->lights);
     cudaFree(d->textures); cudaFree(d->texels); cudaFree(d->partial); cudaFree(d->counters);
     for (cudaEvent_t e : d->ev) if (e) cudaEventDestroy(e);
+    for (void* p : d->pinned) cudaHostUnregister(p);
     delete d;
 }
 
@@ -862,12 +872,12 @@ static int upload_all(HostScene& h, uint64_t* bytes_out) {
     h.dev = d;
     int rc;
     CUDA_TRY(cudaGetDevice(&d->device));
-    if ((rc = upload_vec(h.dprims, (void**)&d->prims, d->bytes)) != RT_OK) return rc;
-    if ((rc = upload_vec(h.dnodes, (void**)&d->nodes, d->bytes)) != RT_OK) return rc;
-    if ((rc = upload_vec(h.dmaterials, (void**)&d->mats, d->bytes)) != RT_OK) return rc;
-    if ((rc = upload_vec(h.dlights, (void**)&d->lights, d->bytes)) != RT_OK) return rc;
-    if ((rc = upload_vec(h.dtextures, (void**)&d->textures, d->bytes)) != RT_OK) return rc;
-    if ((rc = upload_vec(h.texels, (void**)&d->texels, d->bytes)) != RT_OK) return rc;
+    if ((rc = upload_vec(h.dprims, (void**)&d->prims, d->bytes, d)) != RT_OK) return rc;
+    if ((rc = upload_vec(h.dnodes, (void**)&d->nodes, d->bytes, d)) != RT_OK) return rc;
+    if ((rc = upload_vec(h.dmaterials, (void**)&d->mats, d->bytes, d)) != RT_OK) return rc;
+    if ((rc = upload_vec(h.dlights, (void**)&d->lights, d->bytes, d)) != RT_OK) return rc;
+    if ((rc = upload_vec(h.dtextures, (void**)&d->textures, d->bytes, d)) != RT_OK) return rc;
+    if ((rc = upload_vec(h.texels, (void**)&d->texels, d->bytes, d)) != RT_OK) return rc;
     CUDA_TRY(cudaMalloc((void**)&d->counters, 16 * sizeof(unsigned long long)));
     for (auto& e : d->ev) CUDA_TRY(cudaEventCreate(&e));
     cudaDeviceProp prop;
@@ -985,6 +995,7 @@ static int render_impl(HostScene& h, const rt_render_params& rp, uint8_t* rgb8, 
     finalize_kernel<<<(n_pix + 255) / 256, 256, 0, stream>>>(k, rgb8, linear);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(d->ev[2], stream));
+    d->timed = true;
 
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
@@ -1026,6 +1037,20 @@ int rt_scene_upload(rt_scene* scene, uint64_t* bytes) {
 int rt_scene_evict(rt_scene* scene) {
     if (!scene) { rtb::set_error("null scene"); return RT_ERR_INVALID; }
     rtb::device_release(*rtb::host_of(scene));
+    return RT_OK;
+}
+
+int rt_scene_last_timing(rt_scene* scene, float* kernel_ms, float* total_ms) {
+    if (!scene) { rtb::set_error("null scene"); return RT_ERR_INVALID; }
+    rtb::DeviceScene* d = rtb::host_of(scene)->dev;
+    if (!d || !d->timed) { rtb::set_error("rt_scene_last_timing: no render has been recorded on this scene"); return RT_ERR_INVALID; }
+    cudaError_t e = cudaEventSynchronize(d->ev[2]);
+    float k = 0.0f, t = 0.0f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&k, d->ev[1], d->ev[2]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, d->ev[0], d->ev[2]);
+    if (e != cudaSuccess) { rtb::set_error(std::string("rt_scene_last_timing: ") + cudaGetErrorString(e)); return RT_ERR_CUDA; }
+    if (kernel_ms) *kernel_ms = k;
+    if (total_ms) *total_ms = t;
     return RT_OK;
 }
 
