@@ -333,7 +333,7 @@ def run_ours(args, wl):
                        "resolution": [width, height]},
             "rays_per_step": rays, "rays": {"primary": n_primary, "shadow": n_shadow, "secondary": n_secondary},
             "kernel_ms_per_step": k_ms, "kernel_mrays_per_s": rays / (k_ms * 1e-3) / 1e6,
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": int(st.launches) * args.steps,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(width * height * 3), "ms_per_step": float(np.mean(e2e_s)) * 1e3},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
