@@ -13,6 +13,7 @@
 // which shapes are tested at all, and hit IDs are only bit-exact with identical leaves.
 #include <algorithm>
 #include <cfloat>
+#include <cmath>
 #include <chrono>
 #include <cstring>
 #include <future>
@@ -144,20 +145,50 @@ void flatten_scene(HostScene& s) {
         d.q[7] = {bits_f((uint32_t)s.order[k]), 0, 0, 0};
     }
 
-    // internal nodes: map tree index -> device node index (pre-order over internal nodes only)
+    s.dnodes.clear();
+    s.dleaves.clear();
     s.dnodes.clear();
     s.root_ref = 0;
     for (int i = 0; i < 3; ++i) { s.root_box.lo[i] = FLT_MAX; s.root_box.hi[i] = -FLT_MAX; }
     if (!s.tree.empty()) {
         s.root_box = s.tree[0].box;
         std::vector<int> dev_index(s.tree.size(), -1);
-        int n_internal = 0;
+        int n_internal = 0, n_leaf = 0;
         for (size_t i = 0; i < s.tree.size(); ++i)
-            if (s.tree[i].left >= 0) dev_index[i] = n_internal++;
+            dev_index[i] = (s.tree[i].left >= 0) ? n_internal++ : n_leaf++;
         auto ref_of = [&](int ti) -> int32_t {
             const TreeNode& t = s.tree[ti];
-            return t.left >= 0 ? dev_index[ti] : leaf_ref(t.first, t.count);
+            return t.left >= 0 ? dev_index[ti] : leaf_ref(dev_index[ti]);
         };
+        // leaf records (pre-order, so neighbouring leaves are neighbours in memory)
+        s.dleaves.assign((size_t)n_leaf, DLeaf{});
+        for (size_t i = 0; i < s.tree.size(); ++i) {
+            const TreeNode& t = s.tree[i];
+            if (t.left >= 0) continue;
+            DLeaf& L = s.dleaves[dev_index[i]];
+            L.l[0] = {t.box.lo[0], t.box.lo[1], t.box.lo[2], bits_f((uint32_t)t.first)};
+            // bits 0-2 count; bits 4+4T..7+4T = which of the (up to 4) primitives have type T
+            uint32_t meta = (uint32_t)t.count;
+            for (int k = 0; k < t.count; ++k) meta |= (1u << k) << (4 + 4 * s.prims[s.order[t.first + k]].type);
+            L.l[1] = {t.box.hi[0], t.box.hi[1], t.box.hi[2], bits_f(meta)};
+            float pb[24];
+            for (int k = 0; k < 4; ++k) {
+                for (int a = 0; a < 3; ++a) { pb[6 * k + a] = FLT_MAX; pb[6 * k + 3 + a] = -FLT_MAX; }
+                if (k >= t.count) continue;
+                const Box& b = s.prims[s.order[t.first + k]].box;
+                for (int a = 0; a < 3; ++a) {
+                    // Culling box: the primitive's own box pushed outward by far more than the
+                    // rounding noise of the intersection routines (~1e-7 relative), so a ray that
+                    // misses it cannot be reported as a hit by the reference's primitive test.
+                    const double ext = (double)b.hi[a] - (double)b.lo[a];
+                    const double mag = std::max(std::fabs((double)b.lo[a]), std::fabs((double)b.hi[a]));
+                    const double pad = 1e-5 * (ext + mag) + 1e-6;
+                    pb[6 * k + a] = std::nextafter((float)((double)b.lo[a] - pad), -FLT_MAX);
+                    pb[6 * k + 3 + a] = std::nextafter((float)((double)b.hi[a] + pad), FLT_MAX);
+                }
+            }
+            for (int q = 0; q < 6; ++q) L.l[2 + q] = {pb[4 * q], pb[4 * q + 1], pb[4 * q + 2], pb[4 * q + 3]};
+        }
         s.dnodes.assign((size_t)n_internal, DNode{});
         for (size_t i = 0; i < s.tree.size(); ++i) {
             const TreeNode& t = s.tree[i];

@@ -35,6 +35,12 @@ namespace rtb {
 
 #define RT_MAX_DEPTH 16
 #define RT_LVL_STRIDE 8
+// Per-lane refill (a finished lane takes a new ray while the others continue) was measured
+// SLOWER than refilling the whole warp at once (885 vs 1174 Mrays/s on configs[1]): it trades
+// ray coherence for occupancy of lanes. Kept as a switch for re-evaluation.
+#ifndef RT_REFILL
+#define RT_REFILL false
+#endif
 enum LevelCounter { L_RAYS = 0, L_RECS = 1, L_WORK_TRACE = 2, L_WORK_SHADOW = 3 };
 enum Total { T_PRIMARY = 0, T_SHADOW = 1, T_SECONDARY = 2, T_NODES = 3, T_PRIMS = 4, T_OVERFLOW = 5 };
 
@@ -166,7 +172,9 @@ __global__ void __launch_bounds__(256) gen_kernel(const __grid_constant__ FrameP
 }
 
 // ---------------------------------------------------------------------------------------------
-// trace_kernel: closest hit for every ray of the level. Persistent warps fetch 32 rays at a time.
+// trace_kernel: closest hit for every ray of the level. Persistent warps; a lane whose ray is
+// finished takes the next one from the warp's pool, so lanes do not idle until the warp's
+// slowest ray is done (ncu, 32 rays per warp at a time: 10-15 of 32 lanes active).
 // ---------------------------------------------------------------------------------------------
 template <bool STATS>
 __global__ void __launch_bounds__(128) trace_kernel(const __grid_constant__ FrameParams p, int level) {
@@ -175,22 +183,29 @@ __global__ void __launch_bounds__(128) trace_kernel(const __grid_constant__ Fram
     const unsigned int n = min(lv[L_RAYS], (unsigned int)p.capacity);
     const float4* __restrict__ q = p.q[level & 1];
     TraceStats st = {0u, 0u};
+    TravState s;
+    s.cur = RT_CUR_IDLE;
+    int stack[RT_STACK];
+    long long ray = -1;
+    unsigned int pool_lo = 0, pool_hi = 0;
+    bool more = true;
     while (true) {
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(lv + L_WORK_TRACE, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const unsigned int i = base + lane;
-        if (i < n) {
-            const float4 a = q[(size_t)i * 3 + 0], b = q[(size_t)i * 3 + 1];
-            Ray r;
-            r.ox = a.x; r.oy = a.y; r.oz = a.z; r.time = a.w;
-            r.dx = b.x; r.dy = b.y; r.dz = b.z;
-            float t;
-            int prim;
-            traverse<false, STATS>(p.bvh, r, 0.0f, t, prim, st);
-            p.hit_prim[i] = prim;
+        if (RT_REFILL ? __any_sync(0xffffffffu, ray < 0) : !__any_sync(0xffffffffu, ray >= 0)) {
+            const long long got = warp_take(lv + L_WORK_TRACE, n, ray < 0, pool_lo, pool_hi, more);
+            if (ray < 0 && got >= 0) {
+                ray = got;
+                const float4 a = q[(size_t)ray * 3 + 0], b = q[(size_t)ray * 3 + 1];
+                Ray r;
+                r.ox = a.x; r.oy = a.y; r.oz = a.z; r.time = a.w;
+                r.dx = b.x; r.dy = b.y; r.dz = b.z;
+                if (trav_begin<false>(p.bvh, s, r, 0.0f, st)) { p.hit_prim[ray] = s.best_prim; ray = -1; }
+            }
+            if (!__any_sync(0xffffffffu, ray >= 0)) {
+                if (!more && pool_lo >= pool_hi) break;
+                continue;
+            }
         }
+        if (trav_step<false, STATS>(p.bvh, s, stack, st)) { p.hit_prim[ray] = s.best_prim; ray = -1; }
     }
     if (STATS) {
         unsigned long long a = st.nodes, b = st.prims;
@@ -356,15 +371,20 @@ __global__ void __launch_bounds__(128) shadow_kernel(const __grid_constant__ Fra
     unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
     const unsigned long long n = (unsigned long long)lv[L_RECS] * (unsigned long long)p.shadow_per_rec;
     TraceStats st = {0u, 0u};
+    TravState s;
+    s.cur = RT_CUR_IDLE;
+    int stack[RT_STACK];
+    long long cur_item = -1;
+    int* vis_slot = nullptr;
+    unsigned int pool_lo = 0, pool_hi = 0;
+    bool more = true;
     while (true) {
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(lv + L_WORK_SHADOW, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if ((unsigned long long)base >= n) break;
-        const unsigned long long item = (unsigned long long)base + lane;
-        if (item < n) {
-            const unsigned int rec = (unsigned int)(item / (unsigned int)p.shadow_per_rec);
-            int k = (int)(item % (unsigned int)p.shadow_per_rec);
+        if (RT_REFILL ? __any_sync(0xffffffffu, cur_item < 0) : !__any_sync(0xffffffffu, cur_item >= 0)) {
+            const long long item = warp_take(lv + L_WORK_SHADOW, n, cur_item < 0, pool_lo, pool_hi, more);
+            if (cur_item < 0 && item >= 0) {
+            cur_item = item;
+            const unsigned int rec = (unsigned int)((unsigned long long)item / (unsigned int)p.shadow_per_rec);
+            int k = (int)((unsigned long long)item % (unsigned int)p.shadow_per_rec);
             int li = 0;
             float4 l0, l1;
             while (true) {  // which light / which of its samples
@@ -391,9 +411,20 @@ __global__ void __launch_bounds__(128) shadow_kernel(const __grid_constant__ Fra
             sr.ox = r0.x + r1.x * 1e-4f; sr.oy = r0.y + r1.y * 1e-4f; sr.oz = r0.z + r1.z * 1e-4f;
             sr.dx = lx; sr.dy = ly; sr.dz = lz;
             sr.time = 0.0f;  // `Ray shadowRay;` keeps the default time (shapes.hpp:28)
-            float bt;
-            int bp;
-            if (!traverse<true, STATS>(p.bvh, sr, light_dist, bt, bp, st)) atomicAdd(p.vis + (size_t)rec * p.n_lights + li, 1);
+            vis_slot = p.vis + (size_t)rec * p.n_lights + li;
+            if (trav_begin<true>(p.bvh, s, sr, light_dist, st)) {
+                if (s.best_prim < 0) atomicAdd(vis_slot, 1);
+                cur_item = -1;
+            }
+            }
+            if (!__any_sync(0xffffffffu, cur_item >= 0)) {
+                if (!more && pool_lo >= pool_hi) break;
+                continue;
+            }
+        }
+        if (trav_step<true, STATS>(p.bvh, s, stack, st)) {
+            if (s.best_prim < 0) atomicAdd(vis_slot, 1);  // nothing closer than the light: this sample is lit
+            cur_item = -1;
         }
     }
     if (STATS) {
@@ -508,6 +539,7 @@ struct DeviceScene {
     int device = -1;
     float4* prims = nullptr;
     float4* nodes = nullptr;
+    float4* leaves = nullptr;
     float4* mats = nullptr;
     float4* lights = nullptr;
     DTexture* textures = nullptr;
@@ -563,7 +595,7 @@ static int upload_vec(const std::vector<T>& v, void** dst, uint64_t& bytes, Devi
 
 static void free_device(DeviceScene* d) {
     if (!d) return;
-    cudaFree(d->prims); cudaFree(d->nodes); cudaFree(d->mats); cudaFree(d->lights);
+    cudaFree(d->prims); cudaFree(d->nodes); cudaFree(d->leaves); cudaFree(d->mats); cudaFree(d->lights);
     cudaFree(d->textures); cudaFree(d->texels);
     cudaFree(d->q[0]); cudaFree(d->q[1]); cudaFree(d->hit_prim); cudaFree(d->recs); cudaFree(d->vis);
     cudaFree(d->accum); cudaFree(d->lvl); cudaFree(d->totals);
@@ -584,6 +616,7 @@ static int upload_all(HostScene& h, uint64_t* bytes_out) {
     CUDA_TRY(cudaGetDevice(&d->device));
     if ((rc = upload_vec(h.dprims, (void**)&d->prims, d->bytes, d)) != RT_OK) return rc;
     if ((rc = upload_vec(h.dnodes, (void**)&d->nodes, d->bytes, d)) != RT_OK) return rc;
+    if ((rc = upload_vec(h.dleaves, (void**)&d->leaves, d->bytes, d)) != RT_OK) return rc;
     if ((rc = upload_vec(h.dmaterials, (void**)&d->mats, d->bytes, d)) != RT_OK) return rc;
     if ((rc = upload_vec(h.dlights, (void**)&d->lights, d->bytes, d)) != RT_OK) return rc;
     if ((rc = upload_vec(h.dtextures, (void**)&d->textures, d->bytes, d)) != RT_OK) return rc;
@@ -760,7 +793,7 @@ static int render_impl(HostScene& h, const rt_render_params& rp, uint8_t* rgb8, 
     DeviceScene* d = h.dev;
     FrameParams k;
     if ((rc = fill_params(h, rp, k)) != RT_OK) return rc;
-    k.bvh.prims = d->prims; k.bvh.nodes = d->nodes;
+    k.bvh.prims = d->prims; k.bvh.nodes = d->nodes; k.bvh.leaves = d->leaves;
     k.mats = d->mats; k.lights = d->lights; k.textures = d->textures; k.texels = d->texels;
     k.hit_ids = hit_ids;
 

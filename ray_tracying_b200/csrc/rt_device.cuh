@@ -167,14 +167,16 @@ RT_DEV bool point_in_triangle(float px, float py, float pz, float ax, float ay, 
 // operations, so the winner's t recomputed in FULL mode is the same value.
 // Primitive record: see scene.hpp (8 x float4, the first 4 are enough for a miss).
 // ---------------------------------------------------------------------------------------------
-template <bool FULL>
+// KNOWN_TYPE >= 0: the caller knows the primitive's type at compile time (the traversal groups a
+// warp's pending tests by type), so only that type's code is generated.
+template <bool FULL, int KNOWN_TYPE = -1>
 RT_DEV bool intersect_prim(const float4* __restrict__ prims, int idx, const Ray& r, Hit& h) {
     const float4* q = prims + (size_t)idx * 8;
     const float4 q0 = __ldg(q + 0);
     const float4 q1 = __ldg(q + 1);
     const float4 q2 = __ldg(q + 2);
     const float4 q3 = __ldg(q + 3);
-    const int type = (int)(__float_as_uint(q0.w) & 3u);
+    const int type = KNOWN_TYPE >= 0 ? KNOWN_TYPE : (int)(__float_as_uint(q0.w) & 3u);
 
     if (type == RT_PLANE) {
         // Plane::intersect (shapes.cpp:444-483); q1..q3 = corners 0..2 (+ corner 3 in .w), q4 = normal
@@ -310,6 +312,7 @@ RT_DEV bool intersect_prim(const float4* __restrict__ prims, int idx, const Ray&
 struct BvhView {
     const float4* __restrict__ prims;
     const float4* __restrict__ nodes;
+    const float4* __restrict__ leaves;  // 8 x float4 per leaf (scene.hpp DLeaf)
     int n_prims;
     int root_ref;
     float root_lo[3], root_hi[3];
@@ -328,73 +331,150 @@ RT_DEV float prune_limit(float best_t) { return best_t * 1.0001f + 1e-4f; }
 
 #define RT_STACK 40
 
-// Tests one child box. Internal children: conservative (or exact when the ray is `slow` / pruning
-// is off). Leaf children: conservative filter, then the exact reference test decides.
-RT_DEV bool child_test(float lox, float loy, float loz, float hix, float hiy, float hiz, int ref, const Ray& r,
-                       const RayAux& a, bool exact_only, float& tnear) {
-    if (exact_only) return box_exact(lox, loy, loz, hix, hiy, hiz, r, tnear);
-    if (!box_maybe(lox, loy, loz, hix, hiy, hiz, a, tnear)) return false;
-    if (ref >= 0) return true;
-    float te;
-    return box_exact(lox, loy, loz, hix, hiy, hiz, r, te);
+// Conservative test with a three-way answer for leaf boxes: 0 = the reference test surely fails,
+// 2 = it surely passes (the interval has more than twice the error bound to spare), 1 = too close
+// to call -> evaluate box_exact.
+RT_DEV int box_classify(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayAux& a) {
+    const float x1 = __fmaf_rn(lox, a.ix, a.nx), x2 = __fmaf_rn(hix, a.ix, a.nx);
+    const float y1 = __fmaf_rn(loy, a.iy, a.ny), y2 = __fmaf_rn(hiy, a.iy, a.ny);
+    const float z1 = __fmaf_rn(loz, a.iz, a.nz), z2 = __fmaf_rn(hiz, a.iz, a.nz);
+    const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
+    const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
+    const float slack = __fmaf_rn(1e-6f, fabsf(tn) + fabsf(tf), a.k);
+    if (!(tn <= tf + slack && tf >= -slack)) return 0;
+    return (tn + slack <= tf - slack && tf - slack >= 0.0f) ? 2 : 1;
 }
 
 // BVH::get_intersection (acceleration.cpp:142-150): closest hit, ties -> first in leaf order.
 // ANY = true: the shadow query of shade() (raytracer.cpp:230-235): true iff some tested shape has
 // t <= max_t (== "closest hit exists and its t is not > light distance").
+//
+// "while-while" traversal: all lanes of a warp first descend through internal nodes (uniform
+// code: one 64-byte node, two conservative box tests), and only when every lane has reached a
+// leaf or finished do they process leaves together (exact leaf-box test, per-primitive culling
+// boxes, primitive tests). This keeps the lanes of a warp in the same code far more often than
+// interleaving the two per lane.
+// Out-of-line copies keep the hot traversal loop small enough for the instruction cache (with
+// everything inlined the trace kernel was 64 KB of SASS, twice the 32 KB L1.5 I-cache, and
+// `no_instruction` was the top stall reason).
+// (arguments by value: a reference parameter of a real call would pin the caller's ray state in
+// local memory)
+__device__ __noinline__ float box_exact_call_impl(float lox, float loy, float loz, float hix, float hiy, float hiz, float ox,
+                                                  float oy, float oz, float dx, float dy, float dz) {
+    Ray r;
+    r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz; r.time = 0.0f;
+    float tn;
+    return box_exact(lox, loy, loz, hix, hiy, hiz, r, tn) ? tn : __int_as_float(0x7fc00000);  // NaN = miss
+}
+RT_DEV bool box_exact_call(float lox, float loy, float loz, float hix, float hiy, float hiz, const Ray& r, float& tnear) {
+    const float t = box_exact_call_impl(lox, loy, loz, hix, hiy, hiz, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz);
+    tnear = t;
+    return t == t;
+}
+
+// BVH::intersect_linear (acceleration.cpp:123-138): every shape, in shape_list order.
+template <bool ANY>
+__device__ __noinline__ int4 traverse_linear_impl(const float4* __restrict__ prims, int n_prims, float ox, float oy, float oz,
+                                                  float dx, float dy, float dz, float time, float max_t) {
+    Ray r;
+    r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz; r.time = time;
+    float best_t = FLT_MAX;
+    int best_prim = -1, tests = 0;
+    for (int i = 0; i < n_prims; ++i) {
+        Hit h;
+        tests++;
+        if (intersect_prim<false>(prims, i, r, h)) {
+            if (ANY) { if (!(h.t > max_t)) return make_int4(1, i, __float_as_int(h.t), tests); }
+            else if (h.t < best_t) { best_t = h.t; best_prim = i; }
+        }
+    }
+    return make_int4(0, best_prim, __float_as_int(best_t), tests);
+}
+template <bool ANY>
+RT_DEV bool traverse_linear(const BvhView& b, const Ray& r, float max_t, float& best_t, int& best_prim, unsigned int& n_tests) {
+    const int4 v = traverse_linear_impl<ANY>(b.prims, b.n_prims, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.time, max_t);
+    if (!ANY) { best_prim = v.y; best_t = __int_as_float(v.z); }
+    n_tests += (unsigned int)v.w;
+    return v.x != 0;
+}
+
 template <bool ANY, bool STATS>
 RT_DEV bool traverse(const BvhView& b, const Ray& r, float max_t, float& best_t, int& best_prim, TraceStats& st) {
     best_t = FLT_MAX;
     best_prim = -1;
     if (b.n_prims == 0) return false;
-    if (!b.use_bvh) {  // BVH::intersect_linear (acceleration.cpp:123-138)
-        for (int i = 0; i < b.n_prims; ++i) {
-            Hit h;
-            if (STATS) st.prims++;
-            if (intersect_prim<false>(b.prims, i, r, h)) {
-                if (ANY) { if (!(h.t > max_t)) return true; }
-                else if (h.t < best_t) { best_t = h.t; best_prim = i; }
-            }
-        }
-        return false;
-    }
+    if (!b.use_bvh) return traverse_linear<ANY>(b, r, max_t, best_t, best_prim, st.prims);
     const RayAux a = make_aux(r);
     const bool exact_only = a.slow || !b.prune;
-    float tn;
-    if (STATS) st.nodes++;
-    if (!box_exact(b.root_lo[0], b.root_lo[1], b.root_lo[2], b.root_hi[0], b.root_hi[1], b.root_hi[2], r, tn)) return false;
+    // No separate root-box test: the root contains every leaf box, so a ray that fails it fails
+    // every (exact) leaf test below as well.
 
     int stack[RT_STACK];
     int sp = 0;
     int cur = b.root_ref;
     float lim = ANY ? prune_limit(max_t) : FLT_MAX;
+    bool done = false;
     while (true) {
-        if (cur >= 0) {
+        // ---- phase 1: internal nodes ----
+        while (cur >= 0) {
             const float4* n = b.nodes + (size_t)cur * 4;
             const float4 na = __ldg(n + 0), nb = __ldg(n + 1), nc = __ldg(n + 2), nd = __ldg(n + 3);
             const int li = __float_as_int(nd.x), ri = __float_as_int(nd.y);
             float tl, tr;
+            bool hl, hr;
             if (STATS) st.nodes += 2;
-            bool hl = child_test(na.x, na.y, na.z, na.w, nb.x, nb.y, li, r, a, exact_only, tl);
-            bool hr = child_test(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, ri, r, a, exact_only, tr);
+            if (exact_only) {
+                hl = box_exact_call(na.x, na.y, na.z, na.w, nb.x, nb.y, r, tl);
+                hr = box_exact_call(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, r, tr);
+            } else {
+                hl = box_maybe(na.x, na.y, na.z, na.w, nb.x, nb.y, a, tl);
+                hr = box_maybe(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, a, tr);
+            }
             if (b.prune) { hl = hl && !(tl > lim); hr = hr && !(tr > lim); }
             if (hl && hr) {
                 const bool left_first = !b.prune || tl <= tr;
                 stack[sp++] = left_first ? ri : li;
                 cur = left_first ? li : ri;
-                continue;
-            } else if (hl) { cur = li; continue; }
-            else if (hr) { cur = ri; continue; }
-        } else {
-            const int code = ~cur;
-            const int first = code >> 3, count = code & 7;
-            for (int k = 0; k < count; ++k) {
-                Hit h;
-                if (STATS) st.prims++;
-                const int idx = first + k;
-                if (intersect_prim<false>(b.prims, idx, r, h)) {
-                    if (ANY) { if (!(h.t > max_t)) return true; }
-                    else if (h.t < best_t || (h.t == best_t && idx < best_prim)) { best_t = h.t; best_prim = idx; lim = prune_limit(best_t); }
+            } else if (hl) {
+                cur = li;
+            } else if (hr) {
+                cur = ri;
+            } else {
+                if (sp == 0) { done = true; break; }
+                cur = stack[--sp];
+            }
+        }
+        if (done) break;
+        // ---- phase 2: one leaf ----
+        {
+            const float4* L = b.leaves + (size_t)(~cur) * 8;
+            const float4 l0 = __ldg(L + 0), l1 = __ldg(L + 1);
+            if (STATS) st.nodes++;
+            int c = exact_only ? 1 : box_classify(l0.x, l0.y, l0.z, l1.x, l1.y, l1.z, a);
+            if (c == 1) { float te; c = box_exact_call(l0.x, l0.y, l0.z, l1.x, l1.y, l1.z, r, te) ? 2 : 0; }
+            if (c == 2) {
+                const int first = __float_as_int(l0.w), count = __float_as_int(l1.w);
+                unsigned int mask = (1u << count) - 1u;
+                if (!exact_only) {
+                    // skip primitives whose (inflated) own box the ray clearly misses or enters too far
+                    const float4 v2 = __ldg(L + 2), v3 = __ldg(L + 3), v4 = __ldg(L + 4);
+                    const float4 v5 = __ldg(L + 5), v6 = __ldg(L + 6), v7 = __ldg(L + 7);
+                    float tp;
+                    if (!(box_maybe(v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, a, tp) && !(tp > lim))) mask &= ~1u;
+                    if (!(box_maybe(v3.z, v3.w, v4.x, v4.y, v4.z, v4.w, a, tp) && !(tp > lim))) mask &= ~2u;
+                    if (!(box_maybe(v5.x, v5.y, v5.z, v5.w, v6.x, v6.y, a, tp) && !(tp > lim))) mask &= ~4u;
+                    if (!(box_maybe(v6.z, v6.w, v7.x, v7.y, v7.z, v7.w, a, tp) && !(tp > lim))) mask &= ~8u;
+                }
+                while (mask) {  // ONE call site of the (large) primitive test
+                    const int k = __ffs(mask) - 1;
+                    mask &= mask - 1u;
+                    Hit h;
+                    if (STATS) st.prims++;
+                    const int idx = first + k;
+                    if (intersect_prim<false>(b.prims, idx, r, h)) {
+                        if (ANY) { if (!(h.t > max_t)) return true; }
+                        else if (h.t < best_t || (h.t == best_t && idx < best_prim)) { best_t = h.t; best_prim = idx; lim = prune_limit(best_t); }
+                    }
                 }
             }
         }
@@ -402,6 +482,176 @@ RT_DEV bool traverse(const BvhView& b, const Ray& r, float max_t, float& best_t,
         cur = stack[--sp];
     }
     return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Resumable traversal: the same algorithm as traverse(), cut into steps so that a persistent
+// warp can hand a finished lane a new ray while its other lanes keep going.
+//   trav_begin : set up the per-ray state
+//   trav_step  : phase 1 (descend internal nodes until a leaf) + phase 2 (that leaf) + pop;
+//                returns true when the ray is finished. For ANY queries best_prim >= 0 then
+//                means "occluded".
+// ---------------------------------------------------------------------------------------------
+#define RT_CUR_IDLE ((int)0x80000000)
+
+struct TravState {
+    Ray r;
+    RayAux a;
+    float max_t;      // ANY: light distance
+    float best_t;
+    float lim;
+    int best_prim;
+    int cur;          // node ref being visited, RT_CUR_IDLE when the lane has no ray
+    int sp;
+    bool exact_only;
+};
+
+template <bool ANY>
+RT_DEV bool trav_begin(const BvhView& b, TravState& s, const Ray& r, float max_t, TraceStats& st) {
+    s.r = r;
+    s.max_t = max_t;
+    s.best_t = FLT_MAX;
+    s.best_prim = -1;
+    s.sp = 0;
+    s.cur = RT_CUR_IDLE;
+    if (b.n_prims == 0) return true;
+    if (!b.use_bvh) {
+        if (traverse_linear<ANY>(b, r, max_t, s.best_t, s.best_prim, st.prims)) s.best_prim = 0;
+        return true;
+    }
+    s.a = make_aux(r);
+    s.exact_only = s.a.slow || !b.prune;
+    s.lim = ANY ? prune_limit(max_t) : FLT_MAX;
+    s.cur = b.root_ref;
+    return false;
+}
+
+// One primitive test of a known type inside the leaf phase (see trav_step).
+template <bool ANY, bool STATS, int TYPE>
+RT_DEV void leaf_tests_of_type(const BvhView& b, TravState& s, unsigned int& pending, unsigned int type_mask, int first,
+                               bool& occluded, TraceStats& st) {
+    unsigned int m = pending & type_mask;
+    while (__any_sync(0xffffffffu, m != 0u)) {  // all 32 lanes are here: one type's routine at a time
+        if (m != 0u) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1u;
+            Hit h;
+            if (STATS) st.prims++;
+            const int idx = first + k;
+            if (intersect_prim<false, TYPE>(b.prims, idx, s.r, h)) {
+                if (ANY) {
+                    if (!(h.t > s.max_t)) { s.best_prim = idx; occluded = true; m = 0u; pending = 0u; }
+                } else if (h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) {
+                    s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
+                }
+            }
+        }
+    }
+}
+
+// MUST be called by all 32 lanes of a warp together (lanes without a ray have cur == RT_CUR_IDLE).
+template <bool ANY, bool STATS>
+RT_DEV bool trav_step(const BvhView& b, TravState& s, int* stack, TraceStats& st) {
+    bool finished = false;
+    // ---- phase 1: internal nodes, until this lane reaches a leaf or runs out of nodes ----
+    while (s.cur >= 0) {
+        const float4* n = b.nodes + (size_t)s.cur * 4;
+        const float4 na = __ldg(n + 0), nb = __ldg(n + 1), nc = __ldg(n + 2), nd = __ldg(n + 3);
+        const int li = __float_as_int(nd.x), ri = __float_as_int(nd.y);
+        float tl, tr;
+        bool hl, hr;
+        if (STATS) st.nodes += 2;
+        if (s.exact_only) {
+            hl = box_exact_call(na.x, na.y, na.z, na.w, nb.x, nb.y, s.r, tl);
+            hr = box_exact_call(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, s.r, tr);
+        } else {
+            hl = box_maybe(na.x, na.y, na.z, na.w, nb.x, nb.y, s.a, tl);
+            hr = box_maybe(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, s.a, tr);
+        }
+        if (b.prune) { hl = hl && !(tl > s.lim); hr = hr && !(tr > s.lim); }
+        if (hl && hr) {
+            const bool left_first = !b.prune || tl <= tr;
+            stack[s.sp++] = left_first ? ri : li;
+            s.cur = left_first ? li : ri;
+        } else if (hl) {
+            s.cur = li;
+        } else if (hr) {
+            s.cur = ri;
+        } else if (s.sp == 0) {
+            s.cur = RT_CUR_IDLE;
+            finished = true;
+        } else {
+            s.cur = stack[--s.sp];
+        }
+    }
+    // ---- phase 2: one leaf per lane (lanes that are idle or just finished carry pending == 0) ----
+    const bool has_leaf = s.cur != RT_CUR_IDLE;
+    unsigned int pending = 0u, meta = 0u;
+    int first = 0;
+    if (has_leaf) {
+        const float4* L = b.leaves + (size_t)(~s.cur) * 8;
+        const float4 l0 = __ldg(L + 0), l1 = __ldg(L + 1);
+        if (STATS) st.nodes++;
+        int c = s.exact_only ? 1 : box_classify(l0.x, l0.y, l0.z, l1.x, l1.y, l1.z, s.a);
+        if (c == 1) { float te; c = box_exact_call(l0.x, l0.y, l0.z, l1.x, l1.y, l1.z, s.r, te) ? 2 : 0; }
+        if (c == 2) {
+            first = __float_as_int(l0.w);
+            meta = __float_as_uint(l1.w);
+            pending = (1u << (meta & 7u)) - 1u;
+            if (!s.exact_only) {
+                // skip primitives whose (inflated) own box the ray clearly misses or enters too far
+                const float4 v2 = __ldg(L + 2), v3 = __ldg(L + 3), v4 = __ldg(L + 4);
+                const float4 v5 = __ldg(L + 5), v6 = __ldg(L + 6), v7 = __ldg(L + 7);
+                float tp;
+                if (!(box_maybe(v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, s.a, tp) && !(tp > s.lim))) pending &= ~1u;
+                if (!(box_maybe(v3.z, v3.w, v4.x, v4.y, v4.z, v4.w, s.a, tp) && !(tp > s.lim))) pending &= ~2u;
+                if (!(box_maybe(v5.x, v5.y, v5.z, v5.w, v6.x, v6.y, s.a, tp) && !(tp > s.lim))) pending &= ~4u;
+                if (!(box_maybe(v6.z, v6.w, v7.x, v7.y, v7.z, v7.w, s.a, tp) && !(tp > s.lim))) pending &= ~8u;
+            }
+        }
+    }
+    // Primitive tests grouped by type across the warp: lanes sit in different leaves whose
+    // primitives have different types; running sphere tests, then cube tests, ... keeps the lanes
+    // in one routine at a time instead of serialising up to four routines per test.
+    bool occluded = false;
+    leaf_tests_of_type<ANY, STATS, RT_SPHERE>(b, s, pending, (meta >> 4) & 15u, first, occluded, st);
+    leaf_tests_of_type<ANY, STATS, RT_CUBE>(b, s, pending, (meta >> 8) & 15u, first, occluded, st);
+    leaf_tests_of_type<ANY, STATS, RT_RECTANGLE>(b, s, pending, (meta >> 12) & 15u, first, occluded, st);
+    leaf_tests_of_type<ANY, STATS, RT_PLANE>(b, s, pending, (meta >> 16) & 15u, first, occluded, st);
+    if (has_leaf) {
+        if (occluded || s.sp == 0) { s.cur = RT_CUR_IDLE; finished = true; }
+        else s.cur = stack[--s.sp];
+    }
+    return finished;
+}
+
+// Warp-level work distribution for persistent kernels: the warp owns a pool [pool_lo, pool_hi)
+// of consecutive item indices (refilled with one atomic per RT_POOL items); every lane that needs
+// an item gets one. Returns the item index or -1. `more` turns false when the global counter has
+// passed n. All 32 lanes must call it together.
+#define RT_POOL 128u
+RT_DEV long long warp_take(unsigned int* counter, unsigned long long n, bool need, unsigned int& pool_lo, unsigned int& pool_hi,
+                           bool& more) {
+    const int lane = threadIdx.x & 31;
+    long long item = -1;
+    unsigned int mask = __ballot_sync(0xffffffffu, need);
+    while (mask != 0u && (pool_lo < pool_hi || more)) {
+        if (pool_lo >= pool_hi) {  // warp-uniform: get the next pool
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(counter, RT_POOL);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((unsigned long long)base >= n) { more = false; break; }
+            pool_lo = base;
+            pool_hi = (unsigned int)min((unsigned long long)base + RT_POOL, n);
+        }
+        const unsigned int avail = pool_hi - pool_lo;
+        const unsigned int rank = (unsigned int)__popc(mask & ((1u << lane) - 1u));
+        const bool mine = need && item < 0 && rank < avail;
+        if (mine) item = (long long)pool_lo + rank;
+        pool_lo += min(avail, (unsigned int)__popc(mask));
+        mask = __ballot_sync(0xffffffffu, need && item < 0);
+    }
+    return item;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -31,9 +31,18 @@ struct alignas(128) DPrim { F4 q[8]; };
 // One internal node = 64 bytes: both children's boxes and references.
 //   a = (L.min.x, L.min.y, L.min.z, L.max.x)  b = (L.max.y, L.max.z, R.min.x, R.min.y)
 //   c = (R.min.z, R.max.x, R.max.y, R.max.z)  d = bits(left_ref, right_ref, 0, 0)
-// ref >= 0: index of an internal node; ref < 0: leaf, ~ref = (first << 3) | count, over the
-// sorted primitive array.
+// ref >= 0: index of an internal node; ref < 0: leaf, ~ref = index into the leaf records.
 struct alignas(64) DNode { F4 a, b, c, d; };
+
+// One leaf of the reference tree (<= 4 primitives) = 128 bytes:
+//   l0 = (box.lo.xyz, bits first primitive)
+//   l1 = (box.hi.xyz, bits meta): meta bits 0-2 = count, bits 4+4T..7+4T = mask of the leaf's
+//        primitives that have type T (so a warp can run one type's test routine at a time)
+//   l2..l7 = 24 floats: for primitive k, floats [6k, 6k+6) = its own box (lo.xyz, hi.xyz),
+//            INFLATED outward, used only to skip primitives the ray clearly misses.
+// The leaf box is the reference's (exact): whether it passes AABB::intersect decides whether the
+// leaf's primitives are tested at all.
+struct alignas(128) DLeaf { F4 l[8]; };
 
 // Material = 64 bytes:
 //   m0 = (diffuse.rgb, k_ambient) m1 = (specular.rgb, k_diffuse)
@@ -46,7 +55,7 @@ struct alignas(16) DLight { F4 l[2]; };
 
 struct DTexture { int32_t width, height; uint32_t offset, pad; };  // offset into the u8 pool
 
-inline int32_t leaf_ref(int first, int count) { return ~((first << 3) | count); }
+inline int32_t leaf_ref(int leaf_index) { return ~leaf_index; }
 
 // ---------------------------------------------------------------------------------------------
 // Host model
@@ -96,6 +105,7 @@ struct HostScene {
     // flattened for the device
     std::vector<DPrim> dprims;    // sorted order
     std::vector<DNode> dnodes;
+    std::vector<DLeaf> dleaves;
     int32_t root_ref = 0;
     Box root_box{};
     std::vector<DMaterial> dmaterials;
