@@ -15,7 +15,7 @@
 // random numbers at all and are compared bit for bit with the real reference
 // (oracle/_ref/ref_driver); stochastic ones are compared statistically with it.
 //
-// Parity pinning: tests/test_oracle_vs_reference.py checks this file against the unmodified
+// Parity pinning: tests/test_oracle_golden.py checks this file against the unmodified
 // reference compiled from /root/reference (hit IDs, hit distances, BVH dump, 8-bit images) and
 // against committed golden vectors generated from it (tests/golden/).
 #include "rt_oracle.h"
