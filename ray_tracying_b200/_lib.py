@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librt_b200.so")
+# RT_B200_LIB: another build of the same library (A/B runs of kernel variants, scripts/ab_variants.sh)
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(_HERE, "librt_b200.so")
 
 RT_OK, RT_ERR_INVALID, RT_ERR_IO, RT_ERR_CUDA, RT_ERR_SCENE = 0, -1, -2, -3, -4
 RT_SPHERE, RT_CUBE, RT_RECTANGLE, RT_PLANE = 0, 1, 2, 3

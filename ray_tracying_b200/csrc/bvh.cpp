@@ -122,6 +122,150 @@ void build_bvh(HostScene& s) {
     s.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+namespace {
+// ---------------------------------------------------------------------------------------------
+// Culling boxes. A primitive's culling box is only used to SKIP its intersection test, so it must
+// contain every ray the reference's test could report as a hit, including hits that exist only
+// through rounding. Bounds (u = 2^-24, D = distance ray origin -> shape):
+//   * every shape: the reported point lies within ~16u (|o| + |c| + D) of both the ray and the
+//     shape (transform and slab rounding; o = ray origin, c = shape position). Ray origins are the
+//     camera / lens or points on shapes, so |o|, |c| and D are bounded by the scene: the pad is
+//     8e-6 G (= 134u G) with G = the largest |x|+|y|+|z| over all boxes and the camera;
+//   * sphere: the discriminant b^2 - 4ac (shapes.cpp:220-225) cancels catastrophically for distant
+//     origins: a ray is accepted up to 7.5u |o_obj|^2 (object units) outside the unit sphere,
+//     i.e. up to Q D^2 in world units with Q = 7.5u s_max / s_min^2 -- a per-primitive
+//     coefficient the traversal multiplies by its own distance bound (stored doubled, and with a
+//     1.5x margin, because the traversal's bound is (|tn|+|tf|)^2 <= 2 D'^2 + 2 diag^2);
+//   * plane: the inside tests tolerate cross(e, P - v) . n >= -1e-6 (shapes.cpp:31-38), i.e. a
+//     point up to 1e-6 (|e_a|+|e_b|) / (2 area) beyond a vertex; degenerate triangles (repeated
+//     corner) accept a whole line, and corner 3 may lie off the plane of corners 0..2 -- such
+//     quads get an unbounded culling box (the test is simply never skipped).
+// `pad` is the static outward push in world units; returns false when the box must be unbounded.
+// ---------------------------------------------------------------------------------------------
+bool cull_pad(const HostPrim& p, double scene_g, double& pad, float& q) {
+    const double u = 5.9604644775390625e-8;
+    q = 0.0f;
+    double ext = 0.0, mag = 0.0;
+    for (int a = 0; a < 3; ++a) {
+        ext = std::max(ext, (double)p.box.hi[a] - (double)p.box.lo[a]);
+        mag = std::max(mag, std::max(std::fabs((double)p.box.lo[a]), std::fabs((double)p.box.hi[a])));
+    }
+    if (!(ext < 1e30) || !(mag < 1e30)) return false;
+    pad = 1e-5 * (ext + mag) + 1e-6 + 8e-6 * scene_g;
+    if (p.type == RT_SPHERE) {
+        double smin = 1e300, smax = 0.0;
+        for (int j = 0; j < 3; ++j) {  // |scale_j| = length of column j of the rotation*scale block
+            const double n = std::sqrt((double)p.o2w[0][j] * p.o2w[0][j] + (double)p.o2w[1][j] * p.o2w[1][j] +
+                                       (double)p.o2w[2][j] * p.o2w[2][j]);
+            smin = std::min(smin, n);
+            smax = std::max(smax, n);
+        }
+        if (!(smin > 1e-12) || !(smax < 1e12)) return false;
+        const double Q = 7.5 * u * smax / (smin * smin);
+        const double qq = 2.0 * 1.5 * Q;
+        if (!(qq < 1e10)) return false;
+        q = (float)qq;
+        if (!((double)q >= qq)) q = std::nextafter(q, FLT_MAX);
+        const double v2 = (double)p.velocity[0] * p.velocity[0] + (double)p.velocity[1] * p.velocity[1] +
+                          (double)p.velocity[2] * p.velocity[2];
+        pad += 2.0 * 1.5 * Q * (12.0 * smax * smax + 2.0 * v2);  // the diag^2 share of the bound
+    } else if (p.type == RT_PLANE) {
+        if (!p.normal_valid) { pad = 0.0; return true; }  // never hit (shapes.cpp:449)
+        const double n[3] = {p.normal[0], p.normal[1], p.normal[2]};
+        auto sub = [](const float* a, const float* b, double* o) { for (int i = 0; i < 3; ++i) o[i] = (double)a[i] - (double)b[i]; };
+        auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+        auto len = [&](const double* a) { return std::sqrt(dot(a, a)); };
+        double h3[3];
+        sub(p.corners[3], p.corners[0], h3);
+        const double off = std::fabs(dot(h3, n));  // corner 3 off the plane of corners 0..2
+        const int tri[2][3] = {{1, 3, 2}, {0, 1, 2}};  // isPointInQuad, shapes.cpp:491-492
+        double worst = 0.0;
+        for (const auto& t : tri) {
+            double e1[3], e2[3], e3[3];
+            sub(p.corners[t[1]], p.corners[t[0]], e1);
+            sub(p.corners[t[2]], p.corners[t[1]], e2);
+            sub(p.corners[t[0]], p.corners[t[2]], e3);
+            const double cr[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+            const double area2 = std::fabs(dot(cr, n));  // twice the projected area
+            const double l1 = len(e1), l2 = len(e2), l3 = len(e3);
+            if (!(area2 > 1e-9 * (l1 + l2 + l3) * (l1 + l2 + l3)) || !(std::min(l1, std::min(l2, l3)) > 1e-7)) return false;
+            worst = std::max(worst, 2e-6 * (l1 + l2 + l3) / area2);
+        }
+        pad += off * 1.001 + worst;
+        if (!(pad < 1e-2 * ext + 1e-3)) return false;  // tolerance comparable to the quad itself: do not cull
+    }
+    return true;
+}
+
+DWide empty_wide() {
+    DWide w;
+    for (float& x : w.f) x = 0.0f;
+    return w;
+}
+
+void set_child_box(DWide& w, int c, const Box& b) {
+    w.f[0 + c] = b.lo[0];  w.f[4 + c] = b.hi[0];
+    w.f[8 + c] = b.lo[1];  w.f[12 + c] = b.hi[1];
+    w.f[16 + c] = b.lo[2]; w.f[20 + c] = b.hi[2];
+}
+
+// Fills wide node `me` (already allocated) for reference tree node `ti`. Children of an inner
+// node get consecutive indices, allocated before descending into them.
+void emit_wide(HostScene& s, int ti, int me, int level, double scene_g) {
+    s.wide_depth = std::max(s.wide_depth, level);
+    DWide w = empty_wide();
+    const TreeNode& t = s.tree[ti];
+    if (t.left < 0) {
+        // reference leaf: children = its primitives (consecutive sorted positions) with culling boxes
+        uint32_t meta = WIDE_LEAF;
+        float qmax = 0.0f;
+        for (int k = 0; k < t.count; ++k) {
+            const HostPrim& p = s.prims[s.order[t.first + k]];
+            Box cb;
+            double pad = 0.0;
+            float q = 0.0f;
+            if (cull_pad(p, scene_g, pad, q)) {
+                for (int a = 0; a < 3; ++a) {
+                    cb.lo[a] = std::nextafter((float)((double)p.box.lo[a] - pad), -FLT_MAX);
+                    cb.hi[a] = std::nextafter((float)((double)p.box.hi[a] + pad), FLT_MAX);
+                }
+            } else {
+                for (int a = 0; a < 3; ++a) { cb.lo[a] = -1e30f; cb.hi[a] = 1e30f; }
+                q = 0.0f;
+            }
+            set_child_box(w, k, cb);
+            meta |= (1u << k) | ((uint32_t)p.type << (16 + 2 * k));
+            qmax = std::max(qmax, q);
+        }
+        w.f[24] = bits_f((uint32_t)t.first);
+        w.f[25] = bits_f(meta);
+        w.f[26] = qmax;
+        s.dwide[me] = w;
+        return;
+    }
+    int slots[4], n = 0;
+    for (int child : {t.left, t.right}) {
+        const TreeNode& c = s.tree[child];
+        if (c.left >= 0) { slots[n++] = c.left; slots[n++] = c.right; }
+        else slots[n++] = child;
+    }
+    const int first = (int)s.dwide.size();
+    if (first + n >= (1 << 30)) throw std::runtime_error("too many BVH nodes");
+    s.dwide.resize((size_t)first + n);
+    uint32_t meta = 0;
+    for (int k = 0; k < n; ++k) {
+        set_child_box(w, k, s.tree[slots[k]].box);
+        meta |= 1u << k;
+        if (s.tree[slots[k]].left < 0) meta |= 16u << k;
+    }
+    w.f[24] = bits_f((uint32_t)first);
+    w.f[25] = bits_f(meta);
+    s.dwide[me] = w;
+    for (int k = 0; k < n; ++k) emit_wide(s, slots[k], first + k, level + 1, scene_g);
+}
+
+}  // namespace
+
 void flatten_scene(HostScene& s) {
     const int n = (int)s.prims.size();
     // primitives in sorted order
@@ -145,63 +289,33 @@ void flatten_scene(HostScene& s) {
         d.q[7] = {bits_f((uint32_t)s.order[k]), 0, 0, 0};
     }
 
-    s.dnodes.clear();
-    s.dleaves.clear();
-    s.dnodes.clear();
-    s.root_ref = 0;
-    for (int i = 0; i < 3; ++i) { s.root_box.lo[i] = FLT_MAX; s.root_box.hi[i] = -FLT_MAX; }
+    s.dwide.clear();
+    s.wide_depth = 0;
     if (!s.tree.empty()) {
-        s.root_box = s.tree[0].box;
-        std::vector<int> dev_index(s.tree.size(), -1);
-        int n_internal = 0, n_leaf = 0;
-        for (size_t i = 0; i < s.tree.size(); ++i)
-            dev_index[i] = (s.tree[i].left >= 0) ? n_internal++ : n_leaf++;
-        auto ref_of = [&](int ti) -> int32_t {
-            const TreeNode& t = s.tree[ti];
-            return t.left >= 0 ? dev_index[ti] : leaf_ref(dev_index[ti]);
-        };
-        // leaf records (pre-order, so neighbouring leaves are neighbours in memory)
-        s.dleaves.assign((size_t)n_leaf, DLeaf{});
-        for (size_t i = 0; i < s.tree.size(); ++i) {
-            const TreeNode& t = s.tree[i];
-            if (t.left >= 0) continue;
-            DLeaf& L = s.dleaves[dev_index[i]];
-            L.l[0] = {t.box.lo[0], t.box.lo[1], t.box.lo[2], bits_f((uint32_t)t.first)};
-            // bits 0-2 count; bits 4+4T..7+4T = which of the (up to 4) primitives have type T
-            uint32_t meta = (uint32_t)t.count;
-            for (int k = 0; k < t.count; ++k) meta |= (1u << k) << (4 + 4 * s.prims[s.order[t.first + k]].type);
-            L.l[1] = {t.box.hi[0], t.box.hi[1], t.box.hi[2], bits_f(meta)};
-            float pb[24];
-            for (int k = 0; k < 4; ++k) {
-                for (int a = 0; a < 3; ++a) { pb[6 * k + a] = FLT_MAX; pb[6 * k + 3 + a] = -FLT_MAX; }
-                if (k >= t.count) continue;
-                const Box& b = s.prims[s.order[t.first + k]].box;
-                for (int a = 0; a < 3; ++a) {
-                    // Culling box: the primitive's own box pushed outward by far more than the
-                    // rounding noise of the intersection routines (~1e-7 relative), so a ray that
-                    // misses it cannot be reported as a hit by the reference's primitive test.
-                    const double ext = (double)b.hi[a] - (double)b.lo[a];
-                    const double mag = std::max(std::fabs((double)b.lo[a]), std::fabs((double)b.hi[a]));
-                    const double pad = 1e-5 * (ext + mag) + 1e-6;
-                    pb[6 * k + a] = std::nextafter((float)((double)b.lo[a] - pad), -FLT_MAX);
-                    pb[6 * k + 3 + a] = std::nextafter((float)((double)b.hi[a] + pad), FLT_MAX);
-                }
-            }
-            for (int q = 0; q < 6; ++q) L.l[2 + q] = {pb[4 * q], pb[4 * q + 1], pb[4 * q + 2], pb[4 * q + 3]};
+        s.dwide.reserve(s.tree.size() / 2 + 2);
+        // bound of |x|+|y|+|z| over every ray origin: the scene box and the camera (+ lens radius)
+        double scene_g = std::fabs((double)s.cam.location[0]) + std::fabs((double)s.cam.location[1]) +
+                         std::fabs((double)s.cam.location[2]) + 2.0 * std::fabs((double)s.cam.aperture);
+        {
+            double g = 0.0;
+            for (int a = 0; a < 3; ++a)
+                g += std::max(std::fabs((double)s.tree[0].box.lo[a]), std::fabs((double)s.tree[0].box.hi[a]));
+            if (g < 1e30) scene_g = std::max(scene_g, g);
         }
-        s.dnodes.assign((size_t)n_internal, DNode{});
-        for (size_t i = 0; i < s.tree.size(); ++i) {
-            const TreeNode& t = s.tree[i];
-            if (t.left < 0) continue;
-            const Box& L = s.tree[t.left].box;
-            const Box& R = s.tree[t.right].box;
-            DNode& d = s.dnodes[dev_index[i]];
-            d.a = {L.lo[0], L.lo[1], L.lo[2], L.hi[0]};
-            d.b = {L.hi[1], L.hi[2], R.lo[0], R.lo[1]};
-            d.c = {R.lo[2], R.hi[0], R.hi[1], R.hi[2]};
-            d.d = {bits_f((uint32_t)ref_of(t.left)), bits_f((uint32_t)ref_of(t.right)), 0, 0};
+        if (s.tree[0].left < 0) {
+            // the whole scene is one reference leaf: a synthetic root with that leaf as its only child
+            s.dwide.resize(2);
+            DWide root = empty_wide();
+            set_child_box(root, 0, s.tree[0].box);
+            root.f[24] = bits_f(1u);
+            root.f[25] = bits_f(1u | 16u);
+            s.dwide[0] = root;
+            s.wide_depth = 1;
+            emit_wide(s, 0, 1, 2, scene_g);
+        } else {
+            s.dwide.resize(1);
+            emit_wide(s, 0, 0, 1, scene_g);
         }
-        s.root_ref = ref_of(0);
     }
 
     s.dmaterials.assign(s.materials.size(), DMaterial{});

@@ -35,11 +35,30 @@ namespace rtb {
 
 #define RT_MAX_DEPTH 16
 #define RT_LVL_STRIDE 8
-// Per-lane refill (a finished lane takes a new ray while the others continue) was measured
-// SLOWER than refilling the whole warp at once (885 vs 1174 Mrays/s on configs[1]): it trades
-// ray coherence for occupancy of lanes. Kept as a switch for re-evaluation.
-#ifndef RT_REFILL
-#define RT_REFILL false
+// Tunables of the traversal loop (wave_loop), overridable with -D for A/B runs:
+//   RT_T_FETCH : idle lanes of a warp are given new rays once at least this many are idle
+//                (refilling a single lane costs a warp-wide fetch + ray set-up for one ray;
+//                waiting for all 32 leaves lanes idle behind the warp's longest ray);
+//   RT_T_PRIM  : the warp runs its primitive phase once this many lanes wait with candidates;
+//   RT_PHASE_MAJORITY : 1 = run the primitive phase whenever at least as many lanes wait for it
+//                as can take a traversal step (instead of the fixed threshold).
+#ifndef RT_T_FETCH
+#define RT_T_FETCH 12
+#endif
+#ifndef RT_T_PRIM
+#define RT_T_PRIM 12
+#endif
+#ifndef RT_PHASE_MAJORITY
+#define RT_PHASE_MAJORITY 0
+#endif
+#ifndef RT_TRACE_THREADS
+#define RT_TRACE_THREADS 128
+#endif
+#ifndef RT_TRACE_MINBLOCKS
+#define RT_TRACE_MINBLOCKS 6
+#endif
+#ifndef RT_STEPS_PER_VOTE
+#define RT_STEPS_PER_VOTE 2
 #endif
 enum LevelCounter { L_RAYS = 0, L_RECS = 1, L_WORK_TRACE = 2, L_WORK_SHADOW = 3 };
 enum Total { T_PRIMARY = 0, T_SHADOW = 1, T_SECONDARY = 2, T_NODES = 3, T_PRIMS = 4, T_OVERFLOW = 5 };
@@ -172,47 +191,92 @@ __global__ void __launch_bounds__(256) gen_kernel(const __grid_constant__ FrameP
 }
 
 // ---------------------------------------------------------------------------------------------
-// trace_kernel: closest hit for every ray of the level. Persistent warps; a lane whose ray is
-// finished takes the next one from the warp's pool, so lanes do not idle until the warp's
-// slowest ray is done (ncu, 32 rays per warp at a time: 10-15 of 32 lanes active).
+// wave_loop: the traversal loop shared by trace_kernel (closest hit) and shadow_kernel (any hit).
+// Persistent warps. Every iteration the warp votes and does ONE of three things together:
+//   fetch : lanes without a ray take the next rays of the warp's pool (one atomic per 128 rays);
+//   step  : lanes with a node to visit test its four children (trav_step: uniform code, 128 B
+//           node, four conservative slab tests, push / pop on the shared-memory stack);
+//   prims : lanes that reached a reference leaf with candidate primitives run the exact
+//           intersection routines, class by class (trav_prims).
+// Lanes waiting for another phase idle for that iteration; the thresholds above bound how long.
+// Src supplies the rays: load(item, ray, max_t) and store(item, state).
 // ---------------------------------------------------------------------------------------------
-template <bool STATS>
-__global__ void __launch_bounds__(128) trace_kernel(const __grid_constant__ FrameParams p, int level) {
-    const int lane = threadIdx.x & 31;
-    unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
-    const unsigned int n = min(lv[L_RAYS], (unsigned int)p.capacity);
-    const float4* __restrict__ q = p.q[level & 1];
-    TraceStats st = {0u, 0u};
+extern __shared__ int rt_stack_smem[];
+
+template <bool ANY, bool STATS, class Src>
+RT_DEV void wave_loop(const BvhView& bvh, Src& src, unsigned int* counter, unsigned long long n, TraceStats& st) {
+    const unsigned int FULL = 0xffffffffu;
+    const unsigned int stride = blockDim.x * (unsigned int)sizeof(int);
     TravState s;
-    s.cur = RT_CUR_IDLE;
-    int stack[RT_STACK];
-    long long ray = -1;
+    s.cur = RT_CUR_NONE;
+    s.pend = 0u;
+    s.sp0 = (unsigned int)__cvta_generic_to_shared(rt_stack_smem + threadIdx.x);
+    s.sp = s.sp0;
+    long long item = -1;
     unsigned int pool_lo = 0, pool_hi = 0;
     bool more = true;
     while (true) {
-        if (RT_REFILL ? __any_sync(0xffffffffu, ray < 0) : !__any_sync(0xffffffffu, ray >= 0)) {
-            const long long got = warp_take(lv + L_WORK_TRACE, n, ray < 0, pool_lo, pool_hi, more);
-            if (ray < 0 && got >= 0) {
-                ray = got;
-                const float4 a = q[(size_t)ray * 3 + 0], b = q[(size_t)ray * 3 + 1];
-                Ray r;
-                r.ox = a.x; r.oy = a.y; r.oz = a.z; r.time = a.w;
-                r.dx = b.x; r.dy = b.y; r.dz = b.z;
-                if (trav_begin<false>(p.bvh, s, r, 0.0f, st)) { p.hit_prim[ray] = s.best_prim; ray = -1; }
-            }
-            if (!__any_sync(0xffffffffu, ray >= 0)) {
-                if (!more && pool_lo >= pool_hi) break;
+        const unsigned int idle = __ballot_sync(FULL, item < 0);
+        if (idle != 0u) {
+            const bool work = more || pool_lo < pool_hi;  // warp-uniform
+            if (!work) {
+                if (idle == FULL) break;
+            } else if (idle == FULL || __popc(idle) >= RT_T_FETCH) {
+                const long long got = warp_take(counter, n, item < 0, pool_lo, pool_hi, more);
+                if (item < 0 && got >= 0) {
+                    item = got;
+                    Ray r;
+                    float max_t;
+                    src.load(item, r, max_t);
+                    if (trav_begin<ANY>(bvh, s, r, max_t, st)) { src.store(item, s); item = -1; }
+                }
                 continue;
             }
         }
-        if (trav_step<false, STATS>(p.bvh, s, stack, st)) { p.hit_prim[ray] = s.best_prim; ray = -1; }
+        const bool has_pend = s.pend != 0u;
+        const bool can_step = item >= 0 && !has_pend && s.cur != RT_CUR_NONE;
+        const unsigned int pm = __ballot_sync(FULL, has_pend), sm = __ballot_sync(FULL, can_step);
+        const bool do_prims = pm != 0u && (sm == 0u || (RT_PHASE_MAJORITY ? __popc(pm) >= __popc(sm) : __popc(pm) >= RT_T_PRIM));
+        if (do_prims) trav_prims<ANY, STATS>(bvh, s, st);
+        else if (can_step) {
+#pragma unroll 1
+            for (int k = 0; k < RT_STEPS_PER_VOTE && s.pend == 0u && s.cur != RT_CUR_NONE; ++k)
+                trav_step<ANY, STATS>(bvh, s, stride, st);
+        }
+        if (item >= 0 && s.pend == 0u && s.cur == RT_CUR_NONE) { src.store(item, s); item = -1; }
     }
-    if (STATS) {
-        unsigned long long a = st.nodes, b = st.prims;
+}
+
+RT_DEV void flush_stats(const FrameParams& p, const TraceStats& st) {
+    unsigned long long a = st.nodes, b = st.prims;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off); }
-        if (lane == 0) { atomicAdd(p.totals + T_NODES, a); atomicAdd(p.totals + T_PRIMS, b); }
+    for (int off = 16; off > 0; off >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(p.totals + T_NODES, a); atomicAdd(p.totals + T_PRIMS, b); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// trace_kernel: closest hit for every ray of the level (BVH::get_intersection for view rays).
+// ---------------------------------------------------------------------------------------------
+struct ViewRays {
+    const float4* __restrict__ q;
+    int* hit_prim;
+    RT_DEV void load(long long item, Ray& r, float& max_t) const {
+        const float4 a = q[(size_t)item * 3 + 0], b = q[(size_t)item * 3 + 1];
+        r.ox = a.x; r.oy = a.y; r.oz = a.z; r.time = a.w;
+        r.dx = b.x; r.dy = b.y; r.dz = b.z;
+        max_t = 0.0f;
     }
+    RT_DEV void store(long long item, const TravState& s) const { hit_prim[item] = s.best_prim; }
+};
+
+template <bool STATS>
+__global__ void __launch_bounds__(RT_TRACE_THREADS, RT_TRACE_MINBLOCKS) trace_kernel(const __grid_constant__ FrameParams p, int level) {
+    unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
+    const unsigned int n = min(lv[L_RAYS], (unsigned int)p.capacity);
+    TraceStats st = {0u, 0u};
+    ViewRays src = {p.q[level & 1], p.hit_prim};
+    wave_loop<false, STATS>(p.bvh, src, lv + L_WORK_TRACE, n, st);
+    if (STATS) flush_stats(p, st);
 }
 
 // Material::getDiffuseColor (material.hpp:99-134)
@@ -361,78 +425,60 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
 }
 
 // ---------------------------------------------------------------------------------------------
-// shadow_kernel: one thread per shadow ray = (shade record, light, light sample). The samples of
-// one record sit in adjacent lanes (same origin, nearby targets), so warps stay coherent.
+// shadow_kernel: one lane per shadow ray = (light, shade record, light sample), LIGHT-MAJOR: the
+// rays of a warp go to the same light from neighbouring surface points (or, for an area light,
+// from one point to neighbouring targets), so they traverse the same part of the tree.
 // shade() raytracer.cpp:201-236.
 // ---------------------------------------------------------------------------------------------
+struct ShadowRays {
+    const FrameParams& p;
+    unsigned int n_recs;
+    int* vis_slot;
+    RT_DEV void load(long long item, Ray& sr, float& max_t) {
+        unsigned long long rest = (unsigned long long)item;
+        int li = 0, cnt = 1;
+        float4 l0, l1;
+        while (true) {  // which light's block of n_recs * cnt items
+            l0 = __ldg(p.lights + 2 * li);
+            l1 = __ldg(p.lights + 2 * li + 1);
+            cnt = (l1.w > 0.0f) ? p.light_samples : 1;
+            const unsigned long long block = (unsigned long long)n_recs * (unsigned int)cnt;
+            if (rest < block) break;
+            rest -= block;
+            ++li;
+        }
+        const unsigned int rec = (unsigned int)(rest / (unsigned int)cnt);
+        const int k = (int)(rest % (unsigned int)cnt);
+        const float4 r0 = p.recs[(size_t)rec * 5 + 0], r1 = p.recs[(size_t)rec * 5 + 1];
+        float tx = l0.x, ty = l0.y, tz = l0.z;
+        const float radius = l1.w;
+        if (radius > 0.0f) {
+            const float4 r4 = p.recs[(size_t)rec * 5 + 4];
+            RngCtx g = {__float_as_uint(r0.w), p.seed_lo, p.seed_hi, __float_as_uint(r4.x)};
+            float rx, ry, rz;
+            random_in_unit_sphere(g, RNG_LIGHT, __float_as_uint(r4.y), ((uint32_t)li << 16) | (uint32_t)k, rx, ry, rz);
+            tx = tx + rx * radius; ty = ty + ry * radius; tz = tz + rz * radius;
+        }
+        float lx = tx - r0.x, ly = ty - r0.y, lz = tz - r0.z;
+        max_t = sqrtf(dot3(lx, ly, lz, lx, ly, lz));  // light_dist
+        normalize3(lx, ly, lz);
+        sr.ox = r0.x + r1.x * 1e-4f; sr.oy = r0.y + r1.y * 1e-4f; sr.oz = r0.z + r1.z * 1e-4f;
+        sr.dx = lx; sr.dy = ly; sr.dz = lz;
+        sr.time = 0.0f;  // `Ray shadowRay;` keeps the default time (shapes.hpp:28)
+        vis_slot = p.vis + (size_t)rec * p.n_lights + li;
+    }
+    // nothing closer than the light: this sample is lit (raytracer.cpp:233-235)
+    RT_DEV void store(long long, const TravState& s) const { if (s.best_prim < 0) atomicAdd(vis_slot, 1); }
+};
+
 template <bool STATS>
-__global__ void __launch_bounds__(128) shadow_kernel(const __grid_constant__ FrameParams p, int level) {
-    const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(RT_TRACE_THREADS, RT_TRACE_MINBLOCKS) shadow_kernel(const __grid_constant__ FrameParams p, int level) {
     unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
     const unsigned long long n = (unsigned long long)lv[L_RECS] * (unsigned long long)p.shadow_per_rec;
     TraceStats st = {0u, 0u};
-    TravState s;
-    s.cur = RT_CUR_IDLE;
-    int stack[RT_STACK];
-    long long cur_item = -1;
-    int* vis_slot = nullptr;
-    unsigned int pool_lo = 0, pool_hi = 0;
-    bool more = true;
-    while (true) {
-        if (RT_REFILL ? __any_sync(0xffffffffu, cur_item < 0) : !__any_sync(0xffffffffu, cur_item >= 0)) {
-            const long long item = warp_take(lv + L_WORK_SHADOW, n, cur_item < 0, pool_lo, pool_hi, more);
-            if (cur_item < 0 && item >= 0) {
-            cur_item = item;
-            const unsigned int rec = (unsigned int)((unsigned long long)item / (unsigned int)p.shadow_per_rec);
-            int k = (int)((unsigned long long)item % (unsigned int)p.shadow_per_rec);
-            int li = 0;
-            float4 l0, l1;
-            while (true) {  // which light / which of its samples
-                l0 = __ldg(p.lights + 2 * li);
-                l1 = __ldg(p.lights + 2 * li + 1);
-                const int cnt = (l1.w > 0.0f) ? p.light_samples : 1;
-                if (k < cnt) break;
-                k -= cnt;
-                ++li;
-            }
-            const float4 r0 = p.recs[(size_t)rec * 5 + 0], r1 = p.recs[(size_t)rec * 5 + 1], r4 = p.recs[(size_t)rec * 5 + 4];
-            float tx = l0.x, ty = l0.y, tz = l0.z;
-            const float radius = l1.w;
-            if (radius > 0.0f) {
-                RngCtx g = {__float_as_uint(r0.w), p.seed_lo, p.seed_hi, __float_as_uint(r4.x)};
-                float rx, ry, rz;
-                random_in_unit_sphere(g, RNG_LIGHT, __float_as_uint(r4.y), ((uint32_t)li << 16) | (uint32_t)k, rx, ry, rz);
-                tx = tx + rx * radius; ty = ty + ry * radius; tz = tz + rz * radius;
-            }
-            float lx = tx - r0.x, ly = ty - r0.y, lz = tz - r0.z;
-            const float light_dist = sqrtf(dot3(lx, ly, lz, lx, ly, lz));
-            normalize3(lx, ly, lz);
-            Ray sr;
-            sr.ox = r0.x + r1.x * 1e-4f; sr.oy = r0.y + r1.y * 1e-4f; sr.oz = r0.z + r1.z * 1e-4f;
-            sr.dx = lx; sr.dy = ly; sr.dz = lz;
-            sr.time = 0.0f;  // `Ray shadowRay;` keeps the default time (shapes.hpp:28)
-            vis_slot = p.vis + (size_t)rec * p.n_lights + li;
-            if (trav_begin<true>(p.bvh, s, sr, light_dist, st)) {
-                if (s.best_prim < 0) atomicAdd(vis_slot, 1);
-                cur_item = -1;
-            }
-            }
-            if (!__any_sync(0xffffffffu, cur_item >= 0)) {
-                if (!more && pool_lo >= pool_hi) break;
-                continue;
-            }
-        }
-        if (trav_step<true, STATS>(p.bvh, s, stack, st)) {
-            if (s.best_prim < 0) atomicAdd(vis_slot, 1);  // nothing closer than the light: this sample is lit
-            cur_item = -1;
-        }
-    }
-    if (STATS) {
-        unsigned long long a = st.nodes, b = st.prims;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off); }
-        if (lane == 0) { atomicAdd(p.totals + T_NODES, a); atomicAdd(p.totals + T_PRIMS, b); }
-    }
+    ShadowRays src = {p, lv[L_RECS], nullptr};
+    wave_loop<true, STATS>(p.bvh, src, lv + L_WORK_SHADOW, n, st);
+    if (STATS) flush_stats(p, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -538,8 +584,7 @@ __global__ void finalize_kernel(const __grid_constant__ FrameParams p, uint8_t* 
 struct DeviceScene {
     int device = -1;
     float4* prims = nullptr;
-    float4* nodes = nullptr;
-    float4* leaves = nullptr;
+    float* wide = nullptr;
     float4* mats = nullptr;
     float4* lights = nullptr;
     DTexture* textures = nullptr;
@@ -559,7 +604,9 @@ struct DeviceScene {
     long long batch_slots = 3ll << 20;  // (pixel, sample) pairs per batch; halved on queue overflow
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     int sm_count = 0;
-    int trace_blocks = 1, shadow_blocks = 1;  // resident 128-thread blocks per SM
+    int trace_blocks = 1, shadow_blocks = 1;  // resident blocks per SM
+    int stack_depth = 4;
+    size_t stack_bytes = 0;
     bool timed = false;
     int last_launches = 0;
     std::vector<void*> pinned;
@@ -595,7 +642,7 @@ static int upload_vec(const std::vector<T>& v, void** dst, uint64_t& bytes, Devi
 
 static void free_device(DeviceScene* d) {
     if (!d) return;
-    cudaFree(d->prims); cudaFree(d->nodes); cudaFree(d->leaves); cudaFree(d->mats); cudaFree(d->lights);
+    cudaFree(d->prims); cudaFree(d->wide); cudaFree(d->mats); cudaFree(d->lights);
     cudaFree(d->textures); cudaFree(d->texels);
     cudaFree(d->q[0]); cudaFree(d->q[1]); cudaFree(d->hit_prim); cudaFree(d->recs); cudaFree(d->vis);
     cudaFree(d->accum); cudaFree(d->lvl); cudaFree(d->totals);
@@ -615,8 +662,7 @@ static int upload_all(HostScene& h, uint64_t* bytes_out) {
     int rc;
     CUDA_TRY(cudaGetDevice(&d->device));
     if ((rc = upload_vec(h.dprims, (void**)&d->prims, d->bytes, d)) != RT_OK) return rc;
-    if ((rc = upload_vec(h.dnodes, (void**)&d->nodes, d->bytes, d)) != RT_OK) return rc;
-    if ((rc = upload_vec(h.dleaves, (void**)&d->leaves, d->bytes, d)) != RT_OK) return rc;
+    if ((rc = upload_vec(h.dwide, (void**)&d->wide, d->bytes, d)) != RT_OK) return rc;
     if ((rc = upload_vec(h.dmaterials, (void**)&d->mats, d->bytes, d)) != RT_OK) return rc;
     if ((rc = upload_vec(h.dlights, (void**)&d->lights, d->bytes, d)) != RT_OK) return rc;
     if ((rc = upload_vec(h.dtextures, (void**)&d->textures, d->bytes, d)) != RT_OK) return rc;
@@ -627,8 +673,18 @@ static int upload_all(HostScene& h, uint64_t* bytes_out) {
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
     d->sm_count = prop.multiProcessorCount;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_blocks, trace_kernel<false>, 128, 0));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->shadow_blocks, shadow_kernel<false>, 128, 0));
+    // traversal stack in shared memory: at most 3 pushes per inner level of the wide tree
+    d->stack_depth = std::max(4, 3 * std::max(0, h.wide_depth - 1) + 1);
+    d->stack_bytes = (size_t)d->stack_depth * RT_TRACE_THREADS * sizeof(int);
+    if (d->stack_bytes > 200 * 1024) { set_error("BVH too deep for the shared-memory traversal stack"); return RT_ERR_SCENE; }
+    if (d->stack_bytes > 48 * 1024) {
+        CUDA_TRY(cudaFuncSetAttribute(trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
+        CUDA_TRY(cudaFuncSetAttribute(trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
+        CUDA_TRY(cudaFuncSetAttribute(shadow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
+        CUDA_TRY(cudaFuncSetAttribute(shadow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
+    }
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_blocks, trace_kernel<false>, RT_TRACE_THREADS, d->stack_bytes));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->shadow_blocks, shadow_kernel<false>, RT_TRACE_THREADS, d->stack_bytes));
     d->trace_blocks = std::max(1, d->trace_blocks);
     d->shadow_blocks = std::max(1, d->shadow_blocks);
     if (bytes_out) *bytes_out = d->bytes;
@@ -657,12 +713,10 @@ static int fill_params(const HostScene& h, const rt_render_params& rp, FramePara
     if (rp.samples_sqrt > 1024) { set_error("samples_sqrt must be <= 1024"); return RT_ERR_INVALID; }
     std::memset(&k, 0, sizeof(k));
     k.bvh.n_prims = (int)h.dprims.size();
-    k.bvh.root_ref = h.root_ref;
     k.bvh.use_bvh = rp.use_bvh ? 1 : 0;
     k.bvh.prune = (rp.reserved[0] & 1) ? 0 : 1;  // reserved[0] bit 0: literal reference traversal (test hook)
     k.n_lights = (int)h.dlights.size();
     for (int i = 0; i < 3; ++i) {
-        k.bvh.root_lo[i] = h.root_box.lo[i]; k.bvh.root_hi[i] = h.root_box.hi[i];
         k.cam_loc[i] = h.cam.location[i]; k.xdir[i] = h.xdir[i]; k.ydir[i] = h.ydir[i]; k.zdir[i] = h.zdir[i];
     }
     k.focal = h.cam.focal_length;
@@ -765,12 +819,12 @@ static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, uint8_t* 
         gen_kernel<<<std::min(grid_wide, (n_units + 7) / 8), 256, 0, stream>>>(k, u0, n_units);
         ++launches;
         for (int level = 0; level <= k.max_depth; ++level) {
-            if (collect) trace_kernel<true><<<grid_trace, 128, 0, stream>>>(k, level);
-            else trace_kernel<false><<<grid_trace, 128, 0, stream>>>(k, level);
+            if (collect) trace_kernel<true><<<grid_trace, RT_TRACE_THREADS, d->stack_bytes, stream>>>(k, level);
+            else trace_kernel<false><<<grid_trace, RT_TRACE_THREADS, d->stack_bytes, stream>>>(k, level);
             shade_kernel<<<grid_wide, 256, 0, stream>>>(k, level);
             if (k.shadow_per_rec > 0) {
-                if (collect) shadow_kernel<true><<<grid_shadow, 128, 0, stream>>>(k, level);
-                else shadow_kernel<false><<<grid_shadow, 128, 0, stream>>>(k, level);
+                if (collect) shadow_kernel<true><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, stream>>>(k, level);
+                else shadow_kernel<false><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, stream>>>(k, level);
                 ++launches;
             }
             light_kernel<<<grid_wide, 256, 0, stream>>>(k, level);
@@ -793,7 +847,7 @@ static int render_impl(HostScene& h, const rt_render_params& rp, uint8_t* rgb8, 
     DeviceScene* d = h.dev;
     FrameParams k;
     if ((rc = fill_params(h, rp, k)) != RT_OK) return rc;
-    k.bvh.prims = d->prims; k.bvh.nodes = d->nodes; k.bvh.leaves = d->leaves;
+    k.bvh.prims = d->prims; k.bvh.wide = d->wide; k.bvh.stack_depth = d->stack_depth;
     k.mats = d->mats; k.lights = d->lights; k.textures = d->textures; k.texels = d->texels;
     k.hit_ids = hit_ids;
 

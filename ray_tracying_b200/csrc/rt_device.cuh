@@ -11,9 +11,11 @@
 // ray passes, collects ALL leaf hits and returns the first minimum. Ancestor boxes contain leaf
 // boxes and IEEE rounding is monotonic, so a shape is tested iff the box of ITS LEAF passes
 // AABB::intersect. Therefore:
-//   * internal boxes only need a CONSERVATIVE test (never rejects what the reference accepts):
+//   * inner boxes only need a CONSERVATIVE test (never rejects what the reference accepts):
 //     6 FMAs with a precomputed reciprocal instead of 6 IEEE divisions;
-//   * leaf boxes get the conservative test first and, if it passes, the EXACT reference test;
+//   * the box of a reference leaf ("gated" child) gets the conservative test first and, when the
+//     outcome is too close to call, the EXACT reference test;
+//   * a primitive's own (padded) culling box may skip its test when the ray clearly misses it;
 //   * visiting near-first and skipping sub-trees that start beyond the best hit (plus a margin
 //     four orders above rounding noise) cannot change the (t, shape) result.
 #pragma once
@@ -82,41 +84,6 @@ RT_DEV bool box_exact(float lox, float loy, float loz, float hix, float hiy, flo
     return !(tn > tf || tf < 0.0f);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Conservative slab test. t' = fma(plane, 1/d, -o/d). Against the reference's RN(RN(plane-o)/d):
-//     |t' - t| <= 4 eps |t| + 1.01 eps |o/d|      (eps = 2^-24)
-// so accepting when tn' <= tf' + slack and tf' >= -slack with
-//     slack = 1e-6 (|tn'| + |tf'|) + 4e-7 max_i |o_i/d_i| + 1e-30
-// never rejects a box the reference accepts. Rays with a component |d_i| <= 1e-6 (the reference's
-// "parallel" rule) do not use this path at all (RayAux::slow).
-// ---------------------------------------------------------------------------------------------
-struct RayAux {
-    float ix, iy, iz;     // 1/d
-    float nx, ny, nz;     // -o/d
-    float k;              // absolute slack
-    bool slow;            // some |d_i| <= 1e-6: use box_exact everywhere
-};
-
-RT_DEV RayAux make_aux(const Ray& r) {
-    RayAux a;
-    a.slow = fabsf(r.dx) <= 1e-6f || fabsf(r.dy) <= 1e-6f || fabsf(r.dz) <= 1e-6f;
-    a.ix = 1.0f / r.dx; a.iy = 1.0f / r.dy; a.iz = 1.0f / r.dz;
-    a.nx = -(r.ox * a.ix); a.ny = -(r.oy * a.iy); a.nz = -(r.oz * a.iz);
-    a.k = 4e-7f * fmaxf(fmaxf(fabsf(a.nx), fabsf(a.ny)), fabsf(a.nz)) + 1e-30f;
-    return a;
-}
-
-RT_DEV bool box_maybe(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayAux& a, float& tnear) {
-    const float x1 = __fmaf_rn(lox, a.ix, a.nx), x2 = __fmaf_rn(hix, a.ix, a.nx);
-    const float y1 = __fmaf_rn(loy, a.iy, a.ny), y2 = __fmaf_rn(hiy, a.iy, a.ny);
-    const float z1 = __fmaf_rn(loz, a.iz, a.nz), z2 = __fmaf_rn(hiz, a.iz, a.nz);
-    const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
-    const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
-    const float slack = __fmaf_rn(1e-6f, fabsf(tn) + fabsf(tf), a.k);
-    tnear = tn - slack;
-    return tn <= tf + slack && tf >= -slack;
-}
-
 // Shapes::transformPoint with w == 1 (shapes.cpp:151-158) and transformVector (:160-165)
 RT_DEV void xform_point(const float4 r0, const float4 r1, const float4 r2, float x, float y, float z, float& ox, float& oy, float& oz) {
     ox = r0.x * x + r0.y * y + r0.z * z + r0.w;
@@ -167,18 +134,21 @@ RT_DEV bool point_in_triangle(float px, float py, float pz, float ax, float ay, 
 // operations, so the winner's t recomputed in FULL mode is the same value.
 // Primitive record: see scene.hpp (8 x float4, the first 4 are enough for a miss).
 // ---------------------------------------------------------------------------------------------
-// KNOWN_TYPE >= 0: the caller knows the primitive's type at compile time (the traversal groups a
-// warp's pending tests by type), so only that type's code is generated.
-template <bool FULL, int KNOWN_TYPE = -1>
+// CLS: what the caller knows about the primitive's type (the traversal runs a warp's pending tests
+// class by class, so only that class's code is generated at each call site):
+//   PRIM_ANY any type; PRIM_XFORM sphere / cube / rectangle (they share the transform into object
+//   space and back); PRIM_PLANE plane.
+enum PrimClass { PRIM_ANY = 0, PRIM_XFORM = 1, PRIM_PLANE = 2 };
+template <bool FULL, int CLS = PRIM_ANY>
 RT_DEV bool intersect_prim(const float4* __restrict__ prims, int idx, const Ray& r, Hit& h) {
     const float4* q = prims + (size_t)idx * 8;
     const float4 q0 = __ldg(q + 0);
     const float4 q1 = __ldg(q + 1);
     const float4 q2 = __ldg(q + 2);
     const float4 q3 = __ldg(q + 3);
-    const int type = KNOWN_TYPE >= 0 ? KNOWN_TYPE : (int)(__float_as_uint(q0.w) & 3u);
+    const int type = CLS == PRIM_PLANE ? (int)RT_PLANE : (int)(__float_as_uint(q0.w) & 3u);
 
-    if (type == RT_PLANE) {
+    if (CLS != PRIM_XFORM && type == RT_PLANE) {
         // Plane::intersect (shapes.cpp:444-483); q1..q3 = corners 0..2 (+ corner 3 in .w), q4 = normal
         const float4 q4 = __ldg(q + 4);
         if (q4.w == 0.0f) return false;  // |cross| < 1e-6
@@ -307,17 +277,15 @@ RT_DEV bool intersect_prim(const float4* __restrict__ prims, int idx, const Ray&
 }
 
 // ---------------------------------------------------------------------------------------------
-// BVH queries
+// BVH queries over the 4-wide tree (scene.hpp DWide)
 // ---------------------------------------------------------------------------------------------
 struct BvhView {
     const float4* __restrict__ prims;
-    const float4* __restrict__ nodes;
-    const float4* __restrict__ leaves;  // 8 x float4 per leaf (scene.hpp DLeaf)
+    const float* __restrict__ wide;  // 32 floats per node
     int n_prims;
-    int root_ref;
-    float root_lo[3], root_hi[3];
     int use_bvh;
-    int prune;     // 0: visit everything, exact tests only (the reference's literal traversal)
+    int prune;        // 0: visit everything, exact tests only (the reference's literal traversal)
+    int stack_depth;  // entries per thread of the shared-memory traversal stack
 };
 
 struct TraceStats {
@@ -329,34 +297,25 @@ struct TraceStats {
 // (~1e-7 relative), four orders below this margin.
 RT_DEV float prune_limit(float best_t) { return best_t * 1.0001f + 1e-4f; }
 
-#define RT_STACK 40
+#define WIDE_LEAF_BIT 0x100u  // scene.hpp WIDE_LEAF
 
-// Conservative test with a three-way answer for leaf boxes: 0 = the reference test surely fails,
-// 2 = it surely passes (the interval has more than twice the error bound to spare), 1 = too close
-// to call -> evaluate box_exact.
-RT_DEV int box_classify(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayAux& a) {
-    const float x1 = __fmaf_rn(lox, a.ix, a.nx), x2 = __fmaf_rn(hix, a.ix, a.nx);
-    const float y1 = __fmaf_rn(loy, a.iy, a.ny), y2 = __fmaf_rn(hiy, a.iy, a.ny);
-    const float z1 = __fmaf_rn(loz, a.iz, a.nz), z2 = __fmaf_rn(hiz, a.iz, a.nz);
-    const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
-    const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
-    const float slack = __fmaf_rn(1e-6f, fabsf(tn) + fabsf(tf), a.k);
-    if (!(tn <= tf + slack && tf >= -slack)) return 0;
-    return (tn + slack <= tf - slack && tf - slack >= 0.0f) ? 2 : 1;
+struct F8 { float v[8]; };
+// One 256-bit read-only load (sm_100: LDG.E.256): a quarter of a wide node per instruction, i.e.
+// a quarter of the L1 tag look-ups that 16-byte loads would need for the same line.
+RT_DEV F8 ldg256(const float* p) {
+    F8 r;
+#ifdef RT_NO_LDG256
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+#endif
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+        : "l"(p));
+    return r;
 }
 
-// BVH::get_intersection (acceleration.cpp:142-150): closest hit, ties -> first in leaf order.
-// ANY = true: the shadow query of shade() (raytracer.cpp:230-235): true iff some tested shape has
-// t <= max_t (== "closest hit exists and its t is not > light distance").
-//
-// "while-while" traversal: all lanes of a warp first descend through internal nodes (uniform
-// code: one 64-byte node, two conservative box tests), and only when every lane has reached a
-// leaf or finished do they process leaves together (exact leaf-box test, per-primitive culling
-// boxes, primitive tests). This keeps the lanes of a warp in the same code far more often than
-// interleaving the two per lane.
-// Out-of-line copies keep the hot traversal loop small enough for the instruction cache (with
-// everything inlined the trace kernel was 64 KB of SASS, twice the 32 KB L1.5 I-cache, and
-// `no_instruction` was the top stall reason).
+// Out-of-line copies keep the hot traversal loop small (instruction cache) and rare.
 // (arguments by value: a reference parameter of a real call would pin the caller's ray state in
 // local memory)
 __device__ __noinline__ float box_exact_call_impl(float lox, float loy, float loz, float hix, float hiy, float hiz, float ox,
@@ -366,13 +325,13 @@ __device__ __noinline__ float box_exact_call_impl(float lox, float loy, float lo
     float tn;
     return box_exact(lox, loy, loz, hix, hiy, hiz, r, tn) ? tn : __int_as_float(0x7fc00000);  // NaN = miss
 }
-RT_DEV bool box_exact_call(float lox, float loy, float loz, float hix, float hiy, float hiz, const Ray& r, float& tnear) {
+RT_DEV bool box_exact_call(float lox, float loy, float loz, float hix, float hiy, float hiz, const Ray& r) {
     const float t = box_exact_call_impl(lox, loy, loz, hix, hiy, hiz, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz);
-    tnear = t;
     return t == t;
 }
 
 // BVH::intersect_linear (acceleration.cpp:123-138): every shape, in shape_list order.
+// Returns (occluded, best_prim, bits best_t, tests).
 template <bool ANY>
 __device__ __noinline__ int4 traverse_linear_impl(const float4* __restrict__ prims, int n_prims, float ox, float oy, float oz,
                                                   float dx, float dy, float dz, float time, float max_t) {
@@ -390,239 +349,301 @@ __device__ __noinline__ int4 traverse_linear_impl(const float4* __restrict__ pri
     }
     return make_int4(0, best_prim, __float_as_int(best_t), tests);
 }
-template <bool ANY>
-RT_DEV bool traverse_linear(const BvhView& b, const Ray& r, float max_t, float& best_t, int& best_prim, unsigned int& n_tests) {
-    const int4 v = traverse_linear_impl<ANY>(b.prims, b.n_prims, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.time, max_t);
-    if (!ANY) { best_prim = v.y; best_t = __int_as_float(v.z); }
-    n_tests += (unsigned int)v.w;
-    return v.x != 0;
-}
 
-template <bool ANY, bool STATS>
-RT_DEV bool traverse(const BvhView& b, const Ray& r, float max_t, float& best_t, int& best_prim, TraceStats& st) {
-    best_t = FLT_MAX;
-    best_prim = -1;
-    if (b.n_prims == 0) return false;
-    if (!b.use_bvh) return traverse_linear<ANY>(b, r, max_t, best_t, best_prim, st.prims);
-    const RayAux a = make_aux(r);
-    const bool exact_only = a.slow || !b.prune;
-    // No separate root-box test: the root contains every leaf box, so a ray that fails it fails
-    // every (exact) leaf test below as well.
-
-    int stack[RT_STACK];
+// Exact traversal of the wide tree, one lane on its own: the reference's exact box test on every
+// child, no culling boxes, every primitive of every reference leaf whose box passes is tested.
+//   PRUNE = false: the reference's literal traversal (no ordering, no pruning) -- the prune = 0
+//                  validation mode;
+//   PRUNE = true : near-first order and t-pruning with the exact test's own entry parameter --
+//                  for rays the conservative test cannot handle (a direction component with
+//                  |d| <= 1e-6, where the reference tests containment instead of dividing).
+// Returns (occluded, best_prim, bits best_t, primitive tests); box tests in `boxes`.
+template <bool ANY, bool PRUNE>
+__device__ __noinline__ int4 traverse_exact_impl(const float4* __restrict__ prims, const float* __restrict__ wide, float ox,
+                                                 float oy, float oz, float dx, float dy, float dz, float time, float max_t,
+                                                 unsigned int* boxes) {
+    Ray r;
+    r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz; r.time = time;
+    float best_t = FLT_MAX;
+    float lim = (PRUNE && ANY) ? prune_limit(max_t) : FLT_MAX;
+    int best_prim = -1, tests = 0;
+    unsigned int nb = 0;
+    int stack[64];
+    float entry[64];
     int sp = 0;
-    int cur = b.root_ref;
-    float lim = ANY ? prune_limit(max_t) : FLT_MAX;
-    bool done = false;
-    while (true) {
-        // ---- phase 1: internal nodes ----
-        while (cur >= 0) {
-            const float4* n = b.nodes + (size_t)cur * 4;
-            const float4 na = __ldg(n + 0), nb = __ldg(n + 1), nc = __ldg(n + 2), nd = __ldg(n + 3);
-            const int li = __float_as_int(nd.x), ri = __float_as_int(nd.y);
-            float tl, tr;
-            bool hl, hr;
-            if (STATS) st.nodes += 2;
-            if (exact_only) {
-                hl = box_exact_call(na.x, na.y, na.z, na.w, nb.x, nb.y, r, tl);
-                hr = box_exact_call(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, r, tr);
-            } else {
-                hl = box_maybe(na.x, na.y, na.z, na.w, nb.x, nb.y, a, tl);
-                hr = box_maybe(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, a, tr);
-            }
-            if (b.prune) { hl = hl && !(tl > lim); hr = hr && !(tr > lim); }
-            if (hl && hr) {
-                const bool left_first = !b.prune || tl <= tr;
-                stack[sp++] = left_first ? ri : li;
-                cur = left_first ? li : ri;
-            } else if (hl) {
-                cur = li;
-            } else if (hr) {
-                cur = ri;
-            } else {
-                if (sp == 0) { done = true; break; }
-                cur = stack[--sp];
-            }
-        }
-        if (done) break;
-        // ---- phase 2: one leaf ----
-        {
-            const float4* L = b.leaves + (size_t)(~cur) * 8;
-            const float4 l0 = __ldg(L + 0), l1 = __ldg(L + 1);
-            if (STATS) st.nodes++;
-            int c = exact_only ? 1 : box_classify(l0.x, l0.y, l0.z, l1.x, l1.y, l1.z, a);
-            if (c == 1) { float te; c = box_exact_call(l0.x, l0.y, l0.z, l1.x, l1.y, l1.z, r, te) ? 2 : 0; }
-            if (c == 2) {
-                const int first = __float_as_int(l0.w), count = __float_as_int(l1.w);
-                unsigned int mask = (1u << count) - 1u;
-                if (!exact_only) {
-                    // skip primitives whose (inflated) own box the ray clearly misses or enters too far
-                    const float4 v2 = __ldg(L + 2), v3 = __ldg(L + 3), v4 = __ldg(L + 4);
-                    const float4 v5 = __ldg(L + 5), v6 = __ldg(L + 6), v7 = __ldg(L + 7);
-                    float tp;
-                    if (!(box_maybe(v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, a, tp) && !(tp > lim))) mask &= ~1u;
-                    if (!(box_maybe(v3.z, v3.w, v4.x, v4.y, v4.z, v4.w, a, tp) && !(tp > lim))) mask &= ~2u;
-                    if (!(box_maybe(v5.x, v5.y, v5.z, v5.w, v6.x, v6.y, a, tp) && !(tp > lim))) mask &= ~4u;
-                    if (!(box_maybe(v6.z, v6.w, v7.x, v7.y, v7.z, v7.w, a, tp) && !(tp > lim))) mask &= ~8u;
-                }
-                while (mask) {  // ONE call site of the (large) primitive test
-                    const int k = __ffs(mask) - 1;
-                    mask &= mask - 1u;
-                    Hit h;
-                    if (STATS) st.prims++;
-                    const int idx = first + k;
-                    if (intersect_prim<false>(b.prims, idx, r, h)) {
-                        if (ANY) { if (!(h.t > max_t)) return true; }
-                        else if (h.t < best_t || (h.t == best_t && idx < best_prim)) { best_t = h.t; best_prim = idx; lim = prune_limit(best_t); }
+    stack[sp] = 0;
+    entry[sp++] = -FLT_MAX;
+    while (sp > 0) {
+        --sp;
+        if (PRUNE && entry[sp] > lim) continue;
+        const float* w = wide + (size_t)stack[sp] * 32;
+        const int first = __float_as_int(__ldg(w + 24));
+        const unsigned int meta = __float_as_uint(__ldg(w + 25));
+        int child[4];
+        float tn[4];
+        int n = 0;
+        for (int k = 0; k < 4; ++k) {
+            if (!((meta >> k) & 1u)) continue;
+            if (meta & WIDE_LEAF_BIT) {
+                Hit h;
+                tests++;
+                const int idx = first + k;
+                if (intersect_prim<false>(prims, idx, r, h)) {
+                    if (ANY) { if (!(h.t > max_t)) { *boxes = nb; return make_int4(1, idx, __float_as_int(h.t), tests); } }
+                    else if (h.t < best_t || (h.t == best_t && idx < best_prim)) {
+                        best_t = h.t; best_prim = idx;
+                        if (PRUNE) lim = prune_limit(best_t);
                     }
                 }
+            } else {
+                float t;
+                nb++;
+                if (box_exact(__ldg(w + k), __ldg(w + 8 + k), __ldg(w + 16 + k), __ldg(w + 4 + k), __ldg(w + 12 + k),
+                              __ldg(w + 20 + k), r, t) && !(PRUNE && t > lim)) {
+                    int j = n++;  // insertion sort, farthest first
+                    while (PRUNE && j > 0 && tn[j - 1] < t) { tn[j] = tn[j - 1]; child[j] = child[j - 1]; --j; }
+                    tn[j] = t;
+                    child[j] = first + k;
+                }
             }
         }
-        if (sp == 0) break;
-        cur = stack[--sp];
+        for (int j = 0; j < n && sp < 64; ++j) { stack[sp] = child[j]; entry[sp++] = tn[j]; }
     }
-    return false;
+    *boxes = nb;
+    return make_int4(0, best_prim, __float_as_int(best_t), tests);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Resumable traversal: the same algorithm as traverse(), cut into steps so that a persistent
-// warp can hand a finished lane a new ray while its other lanes keep going.
-//   trav_begin : set up the per-ray state
-//   trav_step  : phase 1 (descend internal nodes until a leaf) + phase 2 (that leaf) + pop;
-//                returns true when the ray is finished. For ANY queries best_prim >= 0 then
-//                means "occluded".
+// Per-lane traversal state of the wavefront kernels.
+//
+// Conservative slab test: t' = fma(plane, 1/d_i, -o_i/d_i). Against the reference's
+// RN(RN(plane - o_i) / d_i):
+//     |t' - t| <= 4u |t| + 1.01u |o_i / d_i|                 (u = 2^-24)
+// The second term is a per-axis constant of the ray, so it is folded into the addend: the value
+// that can become the entry parameter of axis i uses -o_i/d_i - e_i, the one that can become the
+// exit parameter -o_i/d_i + e_i, e_i = 2u |o_i/d_i| (n?l / n?h below; which of lo/hi is the entry
+// plane follows from the sign of d_i). Only the relative term is left for the comparison:
+//     slack = 1e-6 (|tn'| + |tf'|) + Q imax (|tn'| + |tf'|)^2
+// Q is zero except for sphere culling boxes (scene.hpp / bvh.cpp cull_pad: the distance-squared
+// rounding term of the sphere test; (|tn'|+|tf'|) bounds the distance to the shape, and
+// imax = max_i |1/d_i| converts the spatial pad into parameter space).
+//   pass   : tn' - tf' <= slack        and  tf' >= -slack       (never rejects what the reference accepts)
+//   surely : tn' - tf' <= -slack - KS  and  tf' >=  slack + KS  (the reference's exact test passes;
+//            KS = 4 max_i e_i undoes the padding of the addends)
+// A gated child (exact box of a reference leaf) that passes but not surely gets the exact test.
+// Rays with a direction component |d_i| <= 1e-6 (the reference's "parallel" rule) never come
+// here (traverse_exact_impl).
 // ---------------------------------------------------------------------------------------------
-#define RT_CUR_IDLE ((int)0x80000000)
+#define RT_CUR_NONE (-1)
+
+// The traversal stack lives in shared memory, one column per thread (entry e of thread t at
+// base + (e * blockDim + t) * 4): TravState::sp is the 32-bit shared-space ADDRESS of the next free
+// entry, so a push is one STS and one add.
+RT_DEV void stack_push(unsigned int& sp, unsigned int stride_bytes, int v) {
+    asm volatile("st.shared.b32 [%0], %1;" :: "r"(sp), "r"(v) : "memory");
+    sp += stride_bytes;
+}
+RT_DEV int stack_pop(unsigned int& sp, unsigned int stride_bytes) {
+    int v;
+    sp -= stride_bytes;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(sp) : "memory");
+    return v;
+}
 
 struct TravState {
     Ray r;
-    RayAux a;
-    float max_t;      // ANY: light distance
+    float ix, iy, iz;     // 1/d
+    float nxl, nyl, nzl;  // -o/d -+ e: addend for the lo planes
+    float nxh, nyh, nzh;  // addend for the hi planes
+    float KS, imax;
+    float max_t;       // ANY: light distance
     float best_t;
     float lim;
-    int best_prim;
-    int cur;          // node ref being visited, RT_CUR_IDLE when the lane has no ray
-    int sp;
-    bool exact_only;
+    int best_prim;     // closest primitive so far; ANY: >= 0 means occluded
+    int cur;           // wide node to visit next, RT_CUR_NONE when there is none
+    unsigned int sp;   // shared-space address of the next free stack entry
+    unsigned int sp0;  // ... of entry 0 (stack empty when sp == sp0)
+    unsigned int pend; // bit k: child k of node pend_node is a primitive waiting for its test
+    int pend_node;
 };
 
+// Sets up a ray. Returns true when the ray is already finished (empty scene, linear scan, exact
+// path); s.best_prim then holds the answer.
 template <bool ANY>
 RT_DEV bool trav_begin(const BvhView& b, TravState& s, const Ray& r, float max_t, TraceStats& st) {
     s.r = r;
     s.max_t = max_t;
     s.best_t = FLT_MAX;
     s.best_prim = -1;
-    s.sp = 0;
-    s.cur = RT_CUR_IDLE;
+    s.sp = s.sp0;
+    s.cur = RT_CUR_NONE;
+    s.pend = 0u;
+    s.pend_node = 0;
     if (b.n_prims == 0) return true;
     if (!b.use_bvh) {
-        if (traverse_linear<ANY>(b, r, max_t, s.best_t, s.best_prim, st.prims)) s.best_prim = 0;
+        const int4 v = traverse_linear_impl<ANY>(b.prims, b.n_prims, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.time, max_t);
+        s.best_prim = ANY ? (v.x ? 0 : -1) : v.y;
+        s.best_t = __int_as_float(v.z);
+        st.prims += (unsigned int)v.w;
         return true;
     }
-    s.a = make_aux(r);
-    s.exact_only = s.a.slow || !b.prune;
+    const bool slow = fabsf(r.dx) <= 1e-6f || fabsf(r.dy) <= 1e-6f || fabsf(r.dz) <= 1e-6f;
+    if (slow || !b.prune) {
+        unsigned int boxes = 0;
+        const int4 v = b.prune ? traverse_exact_impl<ANY, true>(b.prims, b.wide, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.time, max_t, &boxes)
+                               : traverse_exact_impl<ANY, false>(b.prims, b.wide, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.time, max_t, &boxes);
+        s.best_prim = ANY ? (v.x ? 0 : -1) : v.y;
+        s.best_t = __int_as_float(v.z);
+        st.prims += (unsigned int)v.w;
+        st.nodes += boxes;
+        return true;
+    }
+    s.ix = 1.0f / r.dx; s.iy = 1.0f / r.dy; s.iz = 1.0f / r.dz;
+    const float nx = -(r.ox * s.ix), ny = -(r.oy * s.iy), nz = -(r.oz * s.iz);
+    const float ex = 1.2e-7f * fabsf(nx) + 1e-35f, ey = 1.2e-7f * fabsf(ny) + 1e-35f, ez = 1.2e-7f * fabsf(nz) + 1e-35f;
+    // d_i > 0: the lo plane is the entry plane (pad it towards -inf), the hi plane the exit plane
+    s.nxl = s.ix > 0.0f ? nx - ex : nx + ex; s.nxh = s.ix > 0.0f ? nx + ex : nx - ex;
+    s.nyl = s.iy > 0.0f ? ny - ey : ny + ey; s.nyh = s.iy > 0.0f ? ny + ey : ny - ey;
+    s.nzl = s.iz > 0.0f ? nz - ez : nz + ez; s.nzh = s.iz > 0.0f ? nz + ez : nz - ez;
+    s.KS = 4.0f * fmaxf(fmaxf(ex, ey), ez);
+    s.imax = fmaxf(fmaxf(fabsf(s.ix), fabsf(s.iy)), fabsf(s.iz));
     s.lim = ANY ? prune_limit(max_t) : FLT_MAX;
-    s.cur = b.root_ref;
+    s.cur = 0;
     return false;
 }
 
-// One primitive test of a known type inside the leaf phase (see trav_step).
-template <bool ANY, bool STATS, int TYPE>
-RT_DEV void leaf_tests_of_type(const BvhView& b, TravState& s, unsigned int& pending, unsigned int type_mask, int first,
-                               bool& occluded, TraceStats& st) {
-    unsigned int m = pending & type_mask;
-    while (__any_sync(0xffffffffu, m != 0u)) {  // all 32 lanes are here: one type's routine at a time
-        if (m != 0u) {
-            const int k = __ffs(m) - 1;
-            m &= m - 1u;
+// One child of a wide node: conservative slab test. m = min(tf' - tn', tf'): the box passes iff
+// m >= -slack and surely passes iff m >= slack + KS. `ent` = lower bound of the entry parameter.
+// qi = Q * imax of the node (zero unless the node holds spheres).
+RT_DEV void wide_child_test(const TravState& s, float lox, float hix, float loy, float hiy, float loz, float hiz, float qi,
+                            bool& pass, bool& surely, float& ent) {
+    const float x1 = __fmaf_rn(lox, s.ix, s.nxl), x2 = __fmaf_rn(hix, s.ix, s.nxh);
+    const float y1 = __fmaf_rn(loy, s.iy, s.nyl), y2 = __fmaf_rn(hiy, s.iy, s.nyh);
+    const float z1 = __fmaf_rn(loz, s.iz, s.nzl), z2 = __fmaf_rn(hiz, s.iz, s.nzh);
+    const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
+    const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
+    const float sum = fabsf(tn) + fabsf(tf);
+    const float sl = __fmaf_rn(sum, __fmaf_rn(qi, sum, 1e-6f), 1e-30f);  // 1e-6 s + Q imax s^2
+    const float m = fminf(tf - tn, tf);
+    ent = tn - sl;
+    pass = m >= -sl && ent <= s.lim;
+    surely = m >= sl + s.KS;
+}
+
+// Visits node s.cur: tests its (up to) four children. Node children are pushed far-to-near and
+// the nearest becomes s.cur; primitive children (a reference leaf's node) become s.pend. The
+// caller guarantees s.cur != RT_CUR_NONE and s.pend == 0. `stride` = bytes between two stack entries
+// of a thread. Written to compile to straight-line predicated code.
+template <bool ANY, bool STATS>
+RT_DEV void trav_step(const BvhView& b, TravState& s, unsigned int stride, TraceStats& st) {
+    const int node = s.cur;
+    const float* w = b.wide + (size_t)node * 32;
+    const F8 X = ldg256(w), Y = ldg256(w + 8), Z = ldg256(w + 16), C = ldg256(w + 24);
+    if (STATS) st.nodes += 4;
+    const int first = __float_as_int(C.v[0]);
+    const unsigned int meta = __float_as_uint(C.v[1]);
+    const float qi = C.v[2] * s.imax;
+    bool pass[4], sure[4];
+    float ent[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        wide_child_test(s, X.v[k], X.v[4 + k], Y.v[k], Y.v[4 + k], Z.v[k], Z.v[4 + k], qi, pass[k], sure[k], ent[k]);
+    unsigned int pm = ((pass[0] ? 1u : 0u) | (pass[1] ? 2u : 0u) | (pass[2] ? 4u : 0u) | (pass[3] ? 8u : 0u)) & meta;
+    // gated children that pass but not surely: the reference's exact test decides (rare)
+    const unsigned int sm = (sure[0] ? 1u : 0u) | (sure[1] ? 2u : 0u) | (sure[2] ? 4u : 0u) | (sure[3] ? 8u : 0u);
+    unsigned int ex = pm & ~sm & (meta >> 4);
+    while (ex != 0u) {
+        const int k = __ffs(ex) - 1;
+        ex &= ex - 1u;
+        const float* c = w + k;
+        if (!box_exact_call(__ldg(c), __ldg(c + 8), __ldg(c + 16), __ldg(c + 4), __ldg(c + 12), __ldg(c + 20), s.r)) pm &= ~(1u << k);
+    }
+    int next = RT_CUR_NONE;
+    unsigned int sp = s.sp;
+    if (meta & WIDE_LEAF_BIT) {
+        // a reference leaf's node: its passing children wait for the warp's next primitive phase
+        s.pend = pm;
+        s.pend_node = node;
+    } else if (ANY) {
+        // occlusion query: order does not matter
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool p = (pm >> k) & 1u;
+            if (p && next != RT_CUR_NONE) stack_push(sp, stride, next);
+            if (p) next = first + k;
+        }
+    } else {
+        // sort the passing children by entry distance: key = entry bits with the slot in the low 2
+        // bits, compared as SIGNED ints (negative entries -- origin inside the box -- sort first, in
+        // any order among themselves); children that do not pass get the largest key
+        int key[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            key[k] = ((pm >> k) & 1u) ? ((__float_as_int(ent[k]) & ~3) | k) : 0x7fffffff;
+#define RT_CSWAP(i, j) { const int lo_ = min(key[i], key[j]), hi_ = max(key[i], key[j]); key[i] = lo_; key[j] = hi_; }
+        RT_CSWAP(0, 1) RT_CSWAP(2, 3) RT_CSWAP(0, 2) RT_CSWAP(1, 3) RT_CSWAP(1, 2)
+#undef RT_CSWAP
+        const int n = __popc(pm);
+#pragma unroll
+        for (int j = 3; j >= 1; --j) {
+            if (j < n) stack_push(sp, stride, first + (key[j] & 3));
+        }
+        if (n > 0) next = first + (key[0] & 3);
+    }
+    if (next == RT_CUR_NONE && sp != s.sp0) next = stack_pop(sp, stride);
+    s.sp = sp;
+    s.cur = next;
+}
+
+// The warp's primitive phase: every lane with pending primitives tests them, one class of
+// primitive at a time across the warp (transformed shapes, then planes), so that the lanes of a
+// warp run the same intersection routine together. MUST be called by all 32 lanes.
+template <bool ANY, bool STATS>
+RT_DEV void trav_prims(const BvhView& b, TravState& s, TraceStats& st) {
+    unsigned int m_x = 0u, m_p = 0u;
+    int first = 0;
+    if (s.pend != 0u) {
+        const float* w = b.wide + (size_t)s.pend_node * 32;
+        first = __float_as_int(__ldg(w + 24));
+        const unsigned int t = __float_as_uint(__ldg(w + 25)) >> 16;  // 2 bits of type per child
+        const unsigned int pl = ((t & 3u) == 3u ? 1u : 0u) | (((t >> 2) & 3u) == 3u ? 2u : 0u) | (((t >> 4) & 3u) == 3u ? 4u : 0u) |
+                                (((t >> 6) & 3u) == 3u ? 8u : 0u);
+        m_p = s.pend & pl;
+        m_x = s.pend & ~pl;
+        s.pend = 0u;
+    }
+    bool occluded = false;
+    while (__any_sync(0xffffffffu, m_x != 0u)) {
+        if (m_x != 0u) {
+            const int idx = first + __ffs(m_x) - 1;
+            m_x &= m_x - 1u;
             Hit h;
             if (STATS) st.prims++;
-            const int idx = first + k;
-            if (intersect_prim<false, TYPE>(b.prims, idx, s.r, h)) {
+            if (intersect_prim<false, PRIM_XFORM>(b.prims, idx, s.r, h)) {
                 if (ANY) {
-                    if (!(h.t > s.max_t)) { s.best_prim = idx; occluded = true; m = 0u; pending = 0u; }
+                    if (!(h.t > s.max_t)) { occluded = true; m_x = 0u; m_p = 0u; }
                 } else if (h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) {
                     s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
                 }
             }
         }
     }
-}
-
-// MUST be called by all 32 lanes of a warp together (lanes without a ray have cur == RT_CUR_IDLE).
-template <bool ANY, bool STATS>
-RT_DEV bool trav_step(const BvhView& b, TravState& s, int* stack, TraceStats& st) {
-    bool finished = false;
-    // ---- phase 1: internal nodes, until this lane reaches a leaf or runs out of nodes ----
-    while (s.cur >= 0) {
-        const float4* n = b.nodes + (size_t)s.cur * 4;
-        const float4 na = __ldg(n + 0), nb = __ldg(n + 1), nc = __ldg(n + 2), nd = __ldg(n + 3);
-        const int li = __float_as_int(nd.x), ri = __float_as_int(nd.y);
-        float tl, tr;
-        bool hl, hr;
-        if (STATS) st.nodes += 2;
-        if (s.exact_only) {
-            hl = box_exact_call(na.x, na.y, na.z, na.w, nb.x, nb.y, s.r, tl);
-            hr = box_exact_call(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, s.r, tr);
-        } else {
-            hl = box_maybe(na.x, na.y, na.z, na.w, nb.x, nb.y, s.a, tl);
-            hr = box_maybe(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, s.a, tr);
-        }
-        if (b.prune) { hl = hl && !(tl > s.lim); hr = hr && !(tr > s.lim); }
-        if (hl && hr) {
-            const bool left_first = !b.prune || tl <= tr;
-            stack[s.sp++] = left_first ? ri : li;
-            s.cur = left_first ? li : ri;
-        } else if (hl) {
-            s.cur = li;
-        } else if (hr) {
-            s.cur = ri;
-        } else if (s.sp == 0) {
-            s.cur = RT_CUR_IDLE;
-            finished = true;
-        } else {
-            s.cur = stack[--s.sp];
-        }
-    }
-    // ---- phase 2: one leaf per lane (lanes that are idle or just finished carry pending == 0) ----
-    const bool has_leaf = s.cur != RT_CUR_IDLE;
-    unsigned int pending = 0u, meta = 0u;
-    int first = 0;
-    if (has_leaf) {
-        const float4* L = b.leaves + (size_t)(~s.cur) * 8;
-        const float4 l0 = __ldg(L + 0), l1 = __ldg(L + 1);
-        if (STATS) st.nodes++;
-        int c = s.exact_only ? 1 : box_classify(l0.x, l0.y, l0.z, l1.x, l1.y, l1.z, s.a);
-        if (c == 1) { float te; c = box_exact_call(l0.x, l0.y, l0.z, l1.x, l1.y, l1.z, s.r, te) ? 2 : 0; }
-        if (c == 2) {
-            first = __float_as_int(l0.w);
-            meta = __float_as_uint(l1.w);
-            pending = (1u << (meta & 7u)) - 1u;
-            if (!s.exact_only) {
-                // skip primitives whose (inflated) own box the ray clearly misses or enters too far
-                const float4 v2 = __ldg(L + 2), v3 = __ldg(L + 3), v4 = __ldg(L + 4);
-                const float4 v5 = __ldg(L + 5), v6 = __ldg(L + 6), v7 = __ldg(L + 7);
-                float tp;
-                if (!(box_maybe(v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, s.a, tp) && !(tp > s.lim))) pending &= ~1u;
-                if (!(box_maybe(v3.z, v3.w, v4.x, v4.y, v4.z, v4.w, s.a, tp) && !(tp > s.lim))) pending &= ~2u;
-                if (!(box_maybe(v5.x, v5.y, v5.z, v5.w, v6.x, v6.y, s.a, tp) && !(tp > s.lim))) pending &= ~4u;
-                if (!(box_maybe(v6.z, v6.w, v7.x, v7.y, v7.z, v7.w, s.a, tp) && !(tp > s.lim))) pending &= ~8u;
+    while (__any_sync(0xffffffffu, m_p != 0u)) {
+        if (m_p != 0u) {
+            const int idx = first + __ffs(m_p) - 1;
+            m_p &= m_p - 1u;
+            Hit h;
+            if (STATS) st.prims++;
+            if (intersect_prim<false, PRIM_PLANE>(b.prims, idx, s.r, h)) {
+                if (ANY) {
+                    if (!(h.t > s.max_t)) { occluded = true; m_p = 0u; }
+                } else if (h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) {
+                    s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
+                }
             }
         }
     }
-    // Primitive tests grouped by type across the warp: lanes sit in different leaves whose
-    // primitives have different types; running sphere tests, then cube tests, ... keeps the lanes
-    // in one routine at a time instead of serialising up to four routines per test.
-    bool occluded = false;
-    leaf_tests_of_type<ANY, STATS, RT_SPHERE>(b, s, pending, (meta >> 4) & 15u, first, occluded, st);
-    leaf_tests_of_type<ANY, STATS, RT_CUBE>(b, s, pending, (meta >> 8) & 15u, first, occluded, st);
-    leaf_tests_of_type<ANY, STATS, RT_RECTANGLE>(b, s, pending, (meta >> 12) & 15u, first, occluded, st);
-    leaf_tests_of_type<ANY, STATS, RT_PLANE>(b, s, pending, (meta >> 16) & 15u, first, occluded, st);
-    if (has_leaf) {
-        if (occluded || s.sp == 0) { s.cur = RT_CUR_IDLE; finished = true; }
-        else s.cur = stack[--s.sp];
-    }
-    return finished;
+    if (ANY && occluded) { s.best_prim = 0; s.cur = RT_CUR_NONE; s.sp = s.sp0; }
 }
 
 // Warp-level work distribution for persistent kernels: the warp owns a pool [pool_lo, pool_hi)

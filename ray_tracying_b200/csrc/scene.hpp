@@ -28,21 +28,28 @@ struct alignas(16) F4 { float x, y, z, w; };
 // The first 64 bytes are what a miss needs; the second 64 only matter for a hit.
 struct alignas(128) DPrim { F4 q[8]; };
 
-// One internal node = 64 bytes: both children's boxes and references.
-//   a = (L.min.x, L.min.y, L.min.z, L.max.x)  b = (L.max.y, L.max.z, R.min.x, R.min.y)
-//   c = (R.min.z, R.max.x, R.max.y, R.max.z)  d = bits(left_ref, right_ref, 0, 0)
-// ref >= 0: index of an internal node; ref < 0: leaf, ~ref = index into the leaf records.
-struct alignas(64) DNode { F4 a, b, c, d; };
-
-// One leaf of the reference tree (<= 4 primitives) = 128 bytes:
-//   l0 = (box.lo.xyz, bits first primitive)
-//   l1 = (box.hi.xyz, bits meta): meta bits 0-2 = count, bits 4+4T..7+4T = mask of the leaf's
-//        primitives that have type T (so a warp can run one type's test routine at a time)
-//   l2..l7 = 24 floats: for primitive k, floats [6k, 6k+6) = its own box (lo.xyz, hi.xyz),
-//            INFLATED outward, used only to skip primitives the ray clearly misses.
-// The leaf box is the reference's (exact): whether it passes AABB::intersect decides whether the
-// leaf's primitives are tested at all.
-struct alignas(128) DLeaf { F4 l[8]; };
+// One WIDE node = 128 bytes = one L2 line: up to 4 children, structure-of-arrays so that four
+// 256-bit loads fetch it (rt_device.cuh: ldg256):
+//   f[ 0.. 3] = lo.x of children 0..3    f[ 4.. 7] = hi.x
+//   f[ 8..11] = lo.y                     f[12..15] = hi.y
+//   f[16..19] = lo.z                     f[20..23] = hi.z
+//   f[24] = bits: index of child 0 -- the children of a node are CONSECUTIVE (wide nodes
+//           first, first + 1, ... or sorted primitive positions first, first + 1, ...), valid
+//           children occupy slots 0..n-1
+//   f[25] = bits: meta = valid mask (bits 0-3) | gate mask (bits 4-7) | WIDE_LEAF (bit 8) |
+//           primitive types, 2 bits per child (bits 16-23)
+//   f[26] = Q: quadratic cull coefficient of the node's spheres (max over children, else 0)
+//   f[27..31] unused
+// The wide tree is the reference's binary tree (acceleration.cpp:20-64) with every other level
+// skipped; the reference tree itself is kept on the host (tie-break order, leaf boxes, tests).
+//   * inner node: children are wide nodes; a child whose gate bit is set has the EXACT box of a
+//     reference leaf: its primitives may only be tested if that box passes the reference's
+//     AABB::intersect (decided exactly when the conservative test is too close to call);
+//   * WIDE_LEAF node = one reference leaf: children are its primitives, each with its own box
+//     pushed outward (a culling box, see bvh.cpp cull_pad); Q = the coefficient of the
+//     distance-squared rounding term of the sphere test.
+struct alignas(128) DWide { float f[32]; };
+constexpr uint32_t WIDE_LEAF = 0x100u;
 
 // Material = 64 bytes:
 //   m0 = (diffuse.rgb, k_ambient) m1 = (specular.rgb, k_diffuse)
@@ -54,8 +61,6 @@ struct alignas(16) DMaterial { F4 m[4]; };
 struct alignas(16) DLight { F4 l[2]; };
 
 struct DTexture { int32_t width, height; uint32_t offset, pad; };  // offset into the u8 pool
-
-inline int32_t leaf_ref(int leaf_index) { return ~leaf_index; }
 
 // ---------------------------------------------------------------------------------------------
 // Host model
@@ -104,10 +109,8 @@ struct HostScene {
 
     // flattened for the device
     std::vector<DPrim> dprims;    // sorted order
-    std::vector<DNode> dnodes;
-    std::vector<DLeaf> dleaves;
-    int32_t root_ref = 0;
-    Box root_box{};
+    std::vector<DWide> dwide;     // dwide[0] = root (empty when there are no shapes)
+    int wide_depth = 0;           // levels of the wide tree (bounds the traversal stack)
     std::vector<DMaterial> dmaterials;
     std::vector<DLight> dlights;
     std::vector<DTexture> dtextures;
