@@ -109,7 +109,9 @@ typedef struct rt_render_params {
     int32_t rank, world;   /* this process renders screen tiles t with t % world == rank */
     int32_t tile_w, tile_h; /* screen tile size used for that interleave (multiples of 8 and 4) */
     int32_t collect_stats; /* 1: also count node visits / primitive tests (slower) */
-    int32_t reserved[7];
+    int32_t reserved[7];   /* [0] bit 0: literal reference traversal (visit everything, exact tests only; validation)
+                              [1] bit 0: record CUDA events around the trace/shadow/shade/light launches
+                                         (rt_scene_last_kernel_times) */
 } rt_render_params;
 
 typedef struct rt_render_stats {
@@ -168,7 +170,9 @@ int rt_scene_dump_bvh(const rt_scene* scene, rt_bvh_node_dump* out, int32_t max_
  * "scene resident in HBM" state). Idempotent; rt_render* call it on demand. `bytes` (optional)
  * receives the number of bytes copied host->device. */
 int rt_scene_upload(rt_scene* scene, uint64_t* bytes);
-/* Drops the device copy so that the next render uploads again (end-to-end timing). */
+/* Marks the device copy stale so that the next upload / render copies the scene host->device
+ * again (end-to-end timing). Device and page-locked host allocations are kept until
+ * rt_scene_destroy: an upload is one asynchronous copy of one arena. */
 int rt_scene_evict(rt_scene* scene);
 
 /* CUDA-event timings of the most recent rt_render_device / rt_render call on this scene: the
@@ -176,6 +180,11 @@ int rt_scene_evict(rt_scene* scene);
  * the launching stream by every call; this getter waits for them, so it can be used after an
  * asynchronous rt_render_device(stats = NULL) without perturbing the timed region. */
 int rt_scene_last_timing(rt_scene* scene, float* kernel_ms, float* total_ms);
+
+/* Per-kernel-class CUDA-event times of the most recent frame rendered with reserved[1] bit 0 set:
+ * ms4 / launches4 = {trace_kernel, shadow_kernel, shade_kernel, light_kernel} (sum of the launch
+ * durations, number of launches). Events are recorded on the launching stream; waits for them. */
+int rt_scene_last_kernel_times(rt_scene* scene, float* ms4, int32_t* launches4);
 
 /* Number of pixels this rank renders for (rank, world, tile). */
 int rt_shard_pixels(const rt_scene* scene, const rt_render_params* p, int64_t* n_pixels);

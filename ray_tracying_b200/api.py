@@ -42,7 +42,7 @@ class Stats:
 def make_params(use_bvh: bool = False, n_samples_sqrt: int = 4, light_samples: int = 1,
                 max_depth: int = MAX_RECURSION_DEPTH, seed: int = 1, fixed_time: float = -1.0, rank: int = 0,
                 world: int = 1, tile: Sequence[int] = (32, 32), collect_stats: bool = False,
-                prune: bool = True) -> RenderParams:
+                prune: bool = True, time_kernels: bool = False) -> RenderParams:
     """Defaults are the reference binary's (raytracer.cpp:361-363: BVH off, 4x4 samples, 1 light sample)."""
     p = RenderParams()
     lib.rt_render_params_default(C.byref(p))
@@ -56,6 +56,7 @@ def make_params(use_bvh: bool = False, n_samples_sqrt: int = 4, light_samples: i
     p.tile_w, p.tile_h = int(tile[0]), int(tile[1])
     p.collect_stats = int(bool(collect_stats))
     p.reserved[0] = 0 if prune else 1
+    p.reserved[1] = 1 if time_kernels else 0
     return p
 
 
@@ -176,6 +177,12 @@ class Scene:
         check(lib.rt_scene_last_timing(self._h, C.byref(k), C.byref(t)), "rt_scene_last_timing")
         return k.value, t.value
 
+    def last_kernel_times(self) -> dict:
+        """{class: (ms, launches)} of the most recent frame rendered with time_kernels=True."""
+        ms, n = (C.c_float * 4)(), (C.c_int32 * 4)()
+        check(lib.rt_scene_last_kernel_times(self._h, ms, n), "rt_scene_last_kernel_times")
+        return {k: (ms[i], n[i]) for i, k in enumerate(("trace", "shadow", "shade", "light"))}
+
     def shard_pixels(self, params: RenderParams) -> int:
         n = C.c_int64()
         check(lib.rt_shard_pixels(self._h, C.byref(params), C.byref(n)), "rt_shard_pixels")
@@ -192,6 +199,14 @@ class Scene:
         check(lib.rt_render(self._h, C.byref(p), rgb.ctypes.data, ids.ctypes.data if want_ids else None,
                             lin.ctypes.data if want_linear else None, C.byref(st)), "rt_render")
         return rgb, ids, lin, Stats.from_c(st)
+
+    def render_into(self, params: RenderParams, rgb_ptr: int = 0, ids_ptr: int = 0, linear_ptr: int = 0) -> Stats:
+        """Host-buffer render (rt_render) into caller-owned HOST memory given as raw addresses (e.g. a
+        page-locked torch tensor's .data_ptr()): upload if the device copy is stale, render, copy back."""
+        st = RenderStats()
+        check(lib.rt_render(self._h, C.byref(params), rgb_ptr or None, ids_ptr or None, linear_ptr or None, C.byref(st)),
+              "rt_render")
+        return Stats.from_c(st)
 
     def render_device(self, params: RenderParams, rgb_ptr: int = 0, ids_ptr: int = 0, linear_ptr: int = 0,
                       stream: int = 0, sync_stats: bool = True) -> Optional[Stats]:

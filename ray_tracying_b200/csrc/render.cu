@@ -49,7 +49,7 @@ namespace rtb {
 #define RT_T_PRIM 12
 #endif
 #ifndef RT_PHASE_MAJORITY
-#define RT_PHASE_MAJORITY 0
+#define RT_PHASE_MAJORITY 1
 #endif
 #ifndef RT_TRACE_THREADS
 #define RT_TRACE_THREADS 128
@@ -58,7 +58,7 @@ namespace rtb {
 #define RT_TRACE_MINBLOCKS 6
 #endif
 #ifndef RT_STEPS_PER_VOTE
-#define RT_STEPS_PER_VOTE 2
+#define RT_STEPS_PER_VOTE 3
 #endif
 enum LevelCounter { L_RAYS = 0, L_RECS = 1, L_WORK_TRACE = 2, L_WORK_SHADOW = 3 };
 enum Total { T_PRIMARY = 0, T_SHADOW = 1, T_SECONDARY = 2, T_NODES = 3, T_PRIMS = 4, T_OVERFLOW = 5 };
@@ -201,16 +201,17 @@ __global__ void __launch_bounds__(256) gen_kernel(const __grid_constant__ FrameP
 // Lanes waiting for another phase idle for that iteration; the thresholds above bound how long.
 // Src supplies the rays: load(item, ray, max_t) and store(item, state).
 // ---------------------------------------------------------------------------------------------
-extern __shared__ int rt_stack_smem[];
+extern __shared__ __align__(8) int rt_stack_smem[];
 
 template <bool ANY, bool STATS, class Src>
 RT_DEV void wave_loop(const BvhView& bvh, Src& src, unsigned int* counter, unsigned long long n, TraceStats& st) {
     const unsigned int FULL = 0xffffffffu;
-    const unsigned int stride = blockDim.x * (unsigned int)sizeof(int);
+    const unsigned int words = ANY ? 1u : (unsigned int)RT_STACK_WORDS;
+    const unsigned int stride = blockDim.x * words * (unsigned int)sizeof(int);
     TravState s;
     s.cur = RT_CUR_NONE;
     s.pend = 0u;
-    s.sp0 = (unsigned int)__cvta_generic_to_shared(rt_stack_smem + threadIdx.x);
+    s.sp0 = (unsigned int)__cvta_generic_to_shared(rt_stack_smem + threadIdx.x * words);
     s.sp = s.sp0;
     long long item = -1;
     unsigned int pool_lo = 0, pool_hi = 0;
@@ -583,13 +584,20 @@ __global__ void finalize_kernel(const __grid_constant__ FrameParams p, uint8_t* 
 // ---------------------------------------------------------------------------------------------
 struct DeviceScene {
     int device = -1;
+    // The scene lives in ONE device arena filled from ONE page-locked host staging buffer, so
+    // making the scene resident is a single asynchronous H2D copy. Both are allocated once per
+    // scene; rt_scene_evict only marks the device copy stale.
+    uint8_t* arena = nullptr;
+    uint8_t* staging = nullptr;  // cudaMallocHost
+    size_t arena_bytes = 0;
+    bool resident = false;
     float4* prims = nullptr;
     float* wide = nullptr;
     float4* mats = nullptr;
     float4* lights = nullptr;
     DTexture* textures = nullptr;
     uint8_t* texels = nullptr;
-    uint64_t bytes = 0;
+    uint64_t bytes = 0;  // payload bytes (what an upload copies)
     // wavefront buffers
     float4* q[2] = {nullptr, nullptr};
     int* hit_prim = nullptr;
@@ -609,7 +617,15 @@ struct DeviceScene {
     size_t stack_bytes = 0;
     bool timed = false;
     int last_launches = 0;
-    std::vector<void*> pinned;
+    // optional per-kernel-class timing (rt_render_params.reserved[1] & 1): event pairs around the
+    // trace / shadow / shade / light launches of the most recent frame
+    std::vector<cudaEvent_t> class_ev;
+    std::vector<int> class_of;  // class of pair i: 0 trace, 1 shadow, 2 shade, 3 light
+    // frame-sized device outputs of rt_render (host-buffer entry point), kept between calls
+    uint8_t* out_rgb = nullptr;
+    int32_t* out_ids = nullptr;
+    float* out_lin = nullptr;
+    size_t out_pixels = 0;
 };
 
 #define CUDA_TRY(expr)                                                                         \
@@ -621,33 +637,15 @@ struct DeviceScene {
         }                                                                                      \
     } while (0)
 
-template <typename T>
-static int upload_vec(const std::vector<T>& v, void** dst, uint64_t& bytes, DeviceScene* d) {
-    *dst = nullptr;
-    const size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
-    CUDA_TRY(cudaMalloc(dst, n));
-    if (!v.empty()) {
-        // page-lock large host arrays so the copy runs at full PCIe rate (best effort)
-        if (v.size() * sizeof(T) >= (1u << 20)) {
-            if (cudaHostRegister((void*)v.data(), v.size() * sizeof(T), cudaHostRegisterDefault) == cudaSuccess)
-                d->pinned.push_back((void*)v.data());
-            else
-                cudaGetLastError();
-        }
-        CUDA_TRY(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-        bytes += v.size() * sizeof(T);
-    }
-    return RT_OK;
-}
-
 static void free_device(DeviceScene* d) {
     if (!d) return;
-    cudaFree(d->prims); cudaFree(d->wide); cudaFree(d->mats); cudaFree(d->lights);
-    cudaFree(d->textures); cudaFree(d->texels);
+    cudaFree(d->arena);
+    if (d->staging) cudaFreeHost(d->staging);
     cudaFree(d->q[0]); cudaFree(d->q[1]); cudaFree(d->hit_prim); cudaFree(d->recs); cudaFree(d->vis);
     cudaFree(d->accum); cudaFree(d->lvl); cudaFree(d->totals);
+    cudaFree(d->out_rgb); cudaFree(d->out_ids); cudaFree(d->out_lin);
     for (cudaEvent_t e : d->ev) if (e) cudaEventDestroy(e);
-    for (void* p : d->pinned) cudaHostUnregister(p);
+    for (cudaEvent_t e : d->class_ev) if (e) cudaEventDestroy(e);
     delete d;
 }
 
@@ -656,51 +654,83 @@ void device_release(HostScene& h) {
     h.dev = nullptr;
 }
 
-static int upload_all(HostScene& h, uint64_t* bytes_out) {
-    DeviceScene* d = new DeviceScene();
-    h.dev = d;
-    int rc;
-    CUDA_TRY(cudaGetDevice(&d->device));
-    if ((rc = upload_vec(h.dprims, (void**)&d->prims, d->bytes, d)) != RT_OK) return rc;
-    if ((rc = upload_vec(h.dwide, (void**)&d->wide, d->bytes, d)) != RT_OK) return rc;
-    if ((rc = upload_vec(h.dmaterials, (void**)&d->mats, d->bytes, d)) != RT_OK) return rc;
-    if ((rc = upload_vec(h.dlights, (void**)&d->lights, d->bytes, d)) != RT_OK) return rc;
-    if ((rc = upload_vec(h.dtextures, (void**)&d->textures, d->bytes, d)) != RT_OK) return rc;
-    if ((rc = upload_vec(h.texels, (void**)&d->texels, d->bytes, d)) != RT_OK) return rc;
-    CUDA_TRY(cudaMalloc((void**)&d->lvl, (RT_MAX_DEPTH + 2) * RT_LVL_STRIDE * sizeof(unsigned int)));
-    CUDA_TRY(cudaMalloc((void**)&d->totals, 8 * sizeof(unsigned long long)));
-    for (auto& e : d->ev) CUDA_TRY(cudaEventCreate(&e));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
-    d->sm_count = prop.multiProcessorCount;
-    // traversal stack in shared memory: at most 3 pushes per inner level of the wide tree
-    d->stack_depth = std::max(4, 3 * std::max(0, h.wide_depth - 1) + 1);
-    d->stack_bytes = (size_t)d->stack_depth * RT_TRACE_THREADS * sizeof(int);
-    if (d->stack_bytes > 200 * 1024) { set_error("BVH too deep for the shared-memory traversal stack"); return RT_ERR_SCENE; }
-    if (d->stack_bytes > 48 * 1024) {
-        CUDA_TRY(cudaFuncSetAttribute(trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
-        CUDA_TRY(cudaFuncSetAttribute(trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
-        CUDA_TRY(cudaFuncSetAttribute(shadow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
-        CUDA_TRY(cudaFuncSetAttribute(shadow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
+void device_invalidate(HostScene& h) {
+    if (h.dev) h.dev->resident = false;
+}
+
+template <typename T>
+static size_t place(const std::vector<T>& v, size_t& offset) {
+    const size_t at = offset;
+    offset += (std::max<size_t>(v.size(), 1) * sizeof(T) + 255) & ~(size_t)255;
+    return at;
+}
+template <typename T>
+static void stage(uint8_t* staging, size_t at, const std::vector<T>& v, uint64_t& bytes) {
+    if (!v.empty()) std::memcpy(staging + at, v.data(), v.size() * sizeof(T));
+    bytes += v.size() * sizeof(T);
+}
+
+// First call for a scene: allocations, packing of the host arrays into the staging buffer,
+// occupancy queries. Every call: one H2D copy of the arena on `stream` (if not resident).
+static int make_resident(HostScene& h, cudaStream_t stream, uint64_t* bytes_out) {
+    if (bytes_out) *bytes_out = 0;
+    if (!h.dev) {
+        DeviceScene* d = new DeviceScene();
+        h.dev = d;
+        CUDA_TRY(cudaGetDevice(&d->device));
+        size_t off = 0;
+        const size_t o_prims = place(h.dprims, off), o_wide = place(h.dwide, off), o_mats = place(h.dmaterials, off);
+        const size_t o_lights = place(h.dlights, off), o_tex = place(h.dtextures, off), o_texels = place(h.texels, off);
+        d->arena_bytes = off;
+        CUDA_TRY(cudaMalloc((void**)&d->arena, d->arena_bytes));
+        CUDA_TRY(cudaMallocHost((void**)&d->staging, d->arena_bytes));
+        std::memset(d->staging, 0, d->arena_bytes);
+        stage(d->staging, o_prims, h.dprims, d->bytes); stage(d->staging, o_wide, h.dwide, d->bytes);
+        stage(d->staging, o_mats, h.dmaterials, d->bytes); stage(d->staging, o_lights, h.dlights, d->bytes);
+        stage(d->staging, o_tex, h.dtextures, d->bytes); stage(d->staging, o_texels, h.texels, d->bytes);
+        d->prims = (float4*)(d->arena + o_prims); d->wide = (float*)(d->arena + o_wide);
+        d->mats = (float4*)(d->arena + o_mats); d->lights = (float4*)(d->arena + o_lights);
+        d->textures = (DTexture*)(d->arena + o_tex); d->texels = d->arena + o_texels;
+        CUDA_TRY(cudaMalloc((void**)&d->lvl, (RT_MAX_DEPTH + 2) * RT_LVL_STRIDE * sizeof(unsigned int)));
+        CUDA_TRY(cudaMalloc((void**)&d->totals, 8 * sizeof(unsigned long long)));
+        for (auto& e : d->ev) CUDA_TRY(cudaEventCreate(&e));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
+        d->sm_count = prop.multiProcessorCount;
+        // traversal stack in shared memory: at most 3 pushes per inner level of the wide tree
+        d->stack_depth = std::max(4, 3 * std::max(0, h.wide_depth - 1) + 1);
+        d->stack_bytes = (size_t)d->stack_depth * RT_TRACE_THREADS * sizeof(int) * RT_STACK_WORDS;
+        if (d->stack_bytes > 200 * 1024) { set_error("BVH too deep for the shared-memory traversal stack"); return RT_ERR_SCENE; }
+        if (d->stack_bytes > 48 * 1024) {
+            CUDA_TRY(cudaFuncSetAttribute(trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
+            CUDA_TRY(cudaFuncSetAttribute(trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
+            CUDA_TRY(cudaFuncSetAttribute(shadow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
+            CUDA_TRY(cudaFuncSetAttribute(shadow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
+        }
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_blocks, trace_kernel<false>, RT_TRACE_THREADS, d->stack_bytes));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->shadow_blocks, shadow_kernel<false>, RT_TRACE_THREADS, d->stack_bytes));
+        d->trace_blocks = std::max(1, d->trace_blocks);
+        d->shadow_blocks = std::max(1, d->shadow_blocks);
     }
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_blocks, trace_kernel<false>, RT_TRACE_THREADS, d->stack_bytes));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->shadow_blocks, shadow_kernel<false>, RT_TRACE_THREADS, d->stack_bytes));
-    d->trace_blocks = std::max(1, d->trace_blocks);
-    d->shadow_blocks = std::max(1, d->shadow_blocks);
-    if (bytes_out) *bytes_out = d->bytes;
+    DeviceScene* d = h.dev;
+    if (!d->resident) {
+        CUDA_TRY(cudaMemcpyAsync(d->arena, d->staging, d->arena_bytes, cudaMemcpyHostToDevice, stream));
+        d->resident = true;
+        if (bytes_out) *bytes_out = d->bytes;
+    }
     return RT_OK;
 }
 
-static int ensure_uploaded(HostScene& h, uint64_t* bytes_out) {
-    if (h.dev) { if (bytes_out) *bytes_out = 0; return RT_OK; }
+static int ensure_uploaded(HostScene& h, cudaStream_t stream, uint64_t* bytes_out) {
     int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    if (!h.dev && (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)) {
         cudaGetLastError();
         set_error("no CUDA device: the renderer has no CPU fallback");
         return RT_ERR_CUDA;
     }
-    const int rc = upload_all(h, bytes_out);
-    if (rc != RT_OK) device_release(h);  // never keep a half-initialised device scene
+    const bool fresh = h.dev == nullptr;
+    const int rc = make_resident(h, stream, bytes_out);
+    if (rc != RT_OK && fresh) device_release(h);  // never keep a half-initialised device scene
     return rc;
 }
 
@@ -795,7 +825,7 @@ static int ensure_buffers(DeviceScene* d, const FrameParams& k, long long batch_
 }
 
 // Enqueues one frame on `stream` (no host synchronisation).
-static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, uint8_t* rgb8, float* linear, cudaStream_t stream) {
+static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time_classes, uint8_t* rgb8, float* linear, cudaStream_t stream) {
     const long long total_units = (long long)k.n_my_tiles * k.sub_per_tile * k.spp;  // unit = 32 (pixel, sample) slots
     const long long batch_units = std::max<long long>(1, std::min<long long>(std::max<long long>(total_units, 1), d->batch_slots / 32));
     int rc = ensure_buffers(d, k, batch_units * 32);
@@ -811,6 +841,24 @@ static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, uint8_t* 
     const int n_pix = k.res_x * k.res_y;
     clear_accum_kernel<<<(n_pix + 255) / 256, 256, 0, stream>>>(k);
     ++launches;
+    d->class_of.clear();
+    const size_t max_pairs = 512;
+    if (time_classes && d->class_ev.size() < 2 * max_pairs) {
+        const size_t have = d->class_ev.size();
+        d->class_ev.resize(2 * max_pairs, nullptr);
+        for (size_t i = have; i < d->class_ev.size(); ++i) CUDA_TRY(cudaEventCreate(&d->class_ev[i]));
+    }
+    auto mark = [&](int cls, bool begin) {  // event before / after a launch of class cls
+        if (!time_classes) return;
+        if (begin) {
+            if (d->class_of.size() >= max_pairs) return;
+            cudaEventRecord(d->class_ev[2 * d->class_of.size()], stream);
+            d->class_of.push_back(cls | 0x100);  // 0x100: waiting for its end event
+        } else if (!d->class_of.empty() && (d->class_of.back() & 0x100)) {
+            cudaEventRecord(d->class_ev[2 * (d->class_of.size() - 1) + 1], stream);
+            d->class_of.back() &= 0xff;
+        }
+    };
     const int grid_trace = d->sm_count * d->trace_blocks;
     const int grid_shadow = d->sm_count * d->shadow_blocks;
     const int grid_wide = d->sm_count * 8;
@@ -819,15 +867,23 @@ static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, uint8_t* 
         gen_kernel<<<std::min(grid_wide, (n_units + 7) / 8), 256, 0, stream>>>(k, u0, n_units);
         ++launches;
         for (int level = 0; level <= k.max_depth; ++level) {
+            mark(0, true);
             if (collect) trace_kernel<true><<<grid_trace, RT_TRACE_THREADS, d->stack_bytes, stream>>>(k, level);
             else trace_kernel<false><<<grid_trace, RT_TRACE_THREADS, d->stack_bytes, stream>>>(k, level);
+            mark(0, false);
+            mark(2, true);
             shade_kernel<<<grid_wide, 256, 0, stream>>>(k, level);
+            mark(2, false);
             if (k.shadow_per_rec > 0) {
+                mark(1, true);
                 if (collect) shadow_kernel<true><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, stream>>>(k, level);
                 else shadow_kernel<false><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, stream>>>(k, level);
+                mark(1, false);
                 ++launches;
             }
+            mark(3, true);
             light_kernel<<<grid_wide, 256, 0, stream>>>(k, level);
+            mark(3, false);
             launches += 3;
         }
         fold_kernel<<<1, 32, 0, stream>>>(k);
@@ -842,7 +898,7 @@ static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, uint8_t* 
 
 static int render_impl(HostScene& h, const rt_render_params& rp, uint8_t* rgb8, int32_t* hit_ids, float* linear,
                        cudaStream_t stream, rt_render_stats* stats) {
-    int rc = ensure_uploaded(h, nullptr);
+    int rc = ensure_uploaded(h, stream, nullptr);
     if (rc != RT_OK) return rc;
     DeviceScene* d = h.dev;
     FrameParams k;
@@ -854,7 +910,7 @@ static int render_impl(HostScene& h, const rt_render_params& rp, uint8_t* rgb8, 
     for (int attempt = 0;; ++attempt) {
         CUDA_TRY(cudaEventRecord(d->ev[0], stream));
         CUDA_TRY(cudaEventRecord(d->ev[1], stream));
-        if ((rc = enqueue_frame(d, k, rp.collect_stats != 0, rgb8, linear, stream)) != RT_OK) return rc;
+        if ((rc = enqueue_frame(d, k, rp.collect_stats != 0, (rp.reserved[1] & 1) != 0, rgb8, linear, stream)) != RT_OK) return rc;
         CUDA_TRY(cudaEventRecord(d->ev[2], stream));
         d->timed = true;
         if (!stats) return RT_OK;  // asynchronous: an overflow would be reported by the next synchronous call
@@ -884,6 +940,62 @@ static int render_impl(HostScene& h, const rt_render_params& rp, uint8_t* rgb8, 
     }
 }
 
+// rt_render: host output buffers. Upload (if the device copy is stale) -> render -> copy back, all
+// on the default stream; frame-sized device buffers are kept between calls. total_ms = CUDA-event
+// time of everything from the upload to the last copy.
+static int render_host(HostScene& h, const rt_render_params& rp, uint8_t* rgb8, int32_t* hit_ids, float* linear,
+                       rt_render_stats* stats) {
+    if (h.cam.res_x <= 0 || h.cam.res_y <= 0) { set_error("Camera resolution is 0. Check scene.json."); return RT_ERR_SCENE; }
+    const cudaStream_t stream = 0;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: the renderer has no CPU fallback");
+        return RT_ERR_CUDA;
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    CUDA_TRY(cudaEventCreate(&e0));
+    cudaError_t ee = cudaEventCreate(&e1);
+    if (ee != cudaSuccess) { cudaEventDestroy(e0); set_error(std::string("cudaEventCreate: ") + cudaGetErrorString(ee)); return RT_ERR_CUDA; }
+    auto body = [&]() -> int {
+        CUDA_TRY(cudaEventRecord(e0, stream));
+        int rc = ensure_uploaded(h, stream, nullptr);
+        if (rc != RT_OK) return rc;
+        DeviceScene* d = h.dev;
+        const size_t n = (size_t)h.cam.res_x * h.cam.res_y;
+        if (n > d->out_pixels) {
+            cudaFree(d->out_rgb); cudaFree(d->out_ids); cudaFree(d->out_lin);
+            d->out_rgb = nullptr; d->out_ids = nullptr; d->out_lin = nullptr; d->out_pixels = 0;
+            CUDA_TRY(cudaMalloc((void**)&d->out_rgb, n * 3));
+            CUDA_TRY(cudaMalloc((void**)&d->out_ids, n * sizeof(int32_t)));
+            CUDA_TRY(cudaMalloc((void**)&d->out_lin, n * 3 * sizeof(float)));
+            d->out_pixels = n;
+        }
+        if (rp.world > 1) {  // pixels outside this rank's tiles stay zero / -1 in the host buffers
+            if (rgb8) CUDA_TRY(cudaMemsetAsync(d->out_rgb, 0, n * 3, stream));
+            if (hit_ids) CUDA_TRY(cudaMemsetAsync(d->out_ids, 0xff, n * sizeof(int32_t), stream));
+            if (linear) CUDA_TRY(cudaMemsetAsync(d->out_lin, 0, n * 3 * sizeof(float), stream));
+        }
+        rt_render_stats local;
+        rc = render_impl(h, rp, rgb8 ? d->out_rgb : nullptr, hit_ids ? d->out_ids : nullptr, linear ? d->out_lin : nullptr, stream, &local);
+        if (rc != RT_OK) return rc;
+        if (rgb8) CUDA_TRY(cudaMemcpyAsync(rgb8, d->out_rgb, n * 3, cudaMemcpyDeviceToHost, stream));
+        if (hit_ids) CUDA_TRY(cudaMemcpyAsync(hit_ids, d->out_ids, n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        if (linear) CUDA_TRY(cudaMemcpyAsync(linear, d->out_lin, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaEventRecord(e1, stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.0f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        local.total_ms = ms;
+        if (stats) *stats = local;
+        return RT_OK;
+    };
+    const int rc = body();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
 }  // namespace rtb
 
 // ---------------------------------------------------------------------------------------------
@@ -899,12 +1011,12 @@ int rt_device_count(void) {
 
 int rt_scene_upload(rt_scene* scene, uint64_t* bytes) {
     if (!scene) { rtb::set_error("null scene"); return RT_ERR_INVALID; }
-    return rtb::ensure_uploaded(*rtb::host_of(scene), bytes);
+    return rtb::ensure_uploaded(*rtb::host_of(scene), 0, bytes);
 }
 
 int rt_scene_evict(rt_scene* scene) {
     if (!scene) { rtb::set_error("null scene"); return RT_ERR_INVALID; }
-    rtb::device_release(*rtb::host_of(scene));
+    rtb::device_invalidate(*rtb::host_of(scene));
     return RT_OK;
 }
 
@@ -919,6 +1031,25 @@ int rt_scene_last_timing(rt_scene* scene, float* kernel_ms, float* total_ms) {
     if (e != cudaSuccess) { rtb::set_error(std::string("rt_scene_last_timing: ") + cudaGetErrorString(e)); return RT_ERR_CUDA; }
     if (kernel_ms) *kernel_ms = k;
     if (total_ms) *total_ms = t;
+    return RT_OK;
+}
+
+int rt_scene_last_kernel_times(rt_scene* scene, float* ms4, int32_t* launches4) {
+    if (!scene) { rtb::set_error("null scene"); return RT_ERR_INVALID; }
+    rtb::DeviceScene* d = rtb::host_of(scene)->dev;
+    if (!d || !d->timed) { rtb::set_error("rt_scene_last_kernel_times: no render has been recorded on this scene"); return RT_ERR_INVALID; }
+    float ms[4] = {0, 0, 0, 0};
+    int32_t n[4] = {0, 0, 0, 0};
+    cudaError_t e = cudaEventSynchronize(d->ev[2]);
+    for (size_t i = 0; e == cudaSuccess && i < d->class_of.size(); ++i) {
+        if (d->class_of[i] & 0x100) continue;
+        float t = 0.0f;
+        e = cudaEventElapsedTime(&t, d->class_ev[2 * i], d->class_ev[2 * i + 1]);
+        ms[d->class_of[i] & 3] += t;
+        n[d->class_of[i] & 3] += 1;
+    }
+    if (e != cudaSuccess) { rtb::set_error(std::string("rt_scene_last_kernel_times: ") + cudaGetErrorString(e)); return RT_ERR_CUDA; }
+    for (int i = 0; i < 4; ++i) { if (ms4) ms4[i] = ms[i]; if (launches4) launches4[i] = n[i]; }
     return RT_OK;
 }
 
@@ -940,53 +1071,7 @@ int rt_render_device(rt_scene* scene, const rt_render_params* p, uint8_t* rgb8, 
 int rt_render(rt_scene* scene, const rt_render_params* p, uint8_t* rgb8, int32_t* hit_ids, float* linear,
               rt_render_stats* stats) {
     if (!scene || !p) { rtb::set_error("null argument"); return RT_ERR_INVALID; }
-    rtb::HostScene& h = *rtb::host_of(scene);
-    if (h.cam.res_x <= 0 || h.cam.res_y <= 0) { rtb::set_error("Camera resolution is 0. Check scene.json."); return RT_ERR_SCENE; }
-    int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
-        cudaGetLastError();
-        rtb::set_error("no CUDA device: the renderer has no CPU fallback");
-        return RT_ERR_CUDA;
-    }
-    const size_t n = (size_t)h.cam.res_x * h.cam.res_y;
-    uint8_t* d_rgb = nullptr;
-    int32_t* d_ids = nullptr;
-    float* d_lin = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    int rc = RT_OK;
-    auto fail = [&](cudaError_t e, const char* what) {
-        rtb::set_error(std::string(what) + ": " + cudaGetErrorString(e));
-        rc = RT_ERR_CUDA;
-    };
-    cudaError_t e;
-    if ((e = cudaEventCreate(&e0)) != cudaSuccess || (e = cudaEventCreate(&e1)) != cudaSuccess) fail(e, "cudaEventCreate");
-    if (rc == RT_OK && (e = cudaEventRecord(e0, 0)) != cudaSuccess) fail(e, "cudaEventRecord");
-    if (rc == RT_OK && rgb8 && (e = cudaMalloc((void**)&d_rgb, n * 3)) != cudaSuccess) fail(e, "cudaMalloc rgb");
-    if (rc == RT_OK && hit_ids && (e = cudaMalloc((void**)&d_ids, n * sizeof(int32_t))) != cudaSuccess) fail(e, "cudaMalloc ids");
-    if (rc == RT_OK && linear && (e = cudaMalloc((void**)&d_lin, n * 3 * sizeof(float))) != cudaSuccess) fail(e, "cudaMalloc linear");
-    if (rc == RT_OK) {
-        // pixels outside this rank's tiles stay zero / -1 in the host buffers
-        if (d_rgb) cudaMemset(d_rgb, 0, n * 3);
-        if (d_ids) cudaMemset(d_ids, 0xff, n * sizeof(int32_t));
-        if (d_lin) cudaMemset(d_lin, 0, n * 3 * sizeof(float));
-    }
-    rt_render_stats local;
-    if (rc == RT_OK) rc = rtb::render_impl(h, *p, d_rgb, d_ids, d_lin, 0, &local);
-    if (rc == RT_OK && d_rgb && (e = cudaMemcpy(rgb8, d_rgb, n * 3, cudaMemcpyDeviceToHost)) != cudaSuccess) fail(e, "cudaMemcpy rgb");
-    if (rc == RT_OK && d_ids && (e = cudaMemcpy(hit_ids, d_ids, n * sizeof(int32_t), cudaMemcpyDeviceToHost)) != cudaSuccess) fail(e, "cudaMemcpy ids");
-    if (rc == RT_OK && d_lin && (e = cudaMemcpy(linear, d_lin, n * 3 * sizeof(float), cudaMemcpyDeviceToHost)) != cudaSuccess) fail(e, "cudaMemcpy linear");
-    if (rc == RT_OK) {
-        cudaEventRecord(e1, 0);
-        cudaEventSynchronize(e1);
-        float ms = 0.0f;
-        cudaEventElapsedTime(&ms, e0, e1);
-        local.total_ms = ms;
-        if (stats) *stats = local;
-    }
-    cudaFree(d_rgb); cudaFree(d_ids); cudaFree(d_lin);
-    if (e0) cudaEventDestroy(e0);
-    if (e1) cudaEventDestroy(e1);
-    return rc;
+    return rtb::render_host(*rtb::host_of(scene), *p, rgb8, hit_ids, linear, stats);
 }
 
 }  // extern "C"

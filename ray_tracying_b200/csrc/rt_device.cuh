@@ -439,6 +439,13 @@ __device__ __noinline__ int4 traverse_exact_impl(const float4* __restrict__ prim
 // The traversal stack lives in shared memory, one column per thread (entry e of thread t at
 // base + (e * blockDim + t) * 4): TravState::sp is the 32-bit shared-space ADDRESS of the next free
 // entry, so a push is one STS and one add.
+// Closest-hit queries store (node, entry parameter) pairs -- RT_STACK_WORDS = 2, one 64-bit
+// access -- so that a popped sub-tree that starts beyond the current best hit is dropped without
+// visiting it; occlusion queries have a fixed limit and store the node only.
+#ifndef RT_STACK_ENTRY_T
+#define RT_STACK_ENTRY_T 1
+#endif
+#define RT_STACK_WORDS (RT_STACK_ENTRY_T ? 2 : 1)
 RT_DEV void stack_push(unsigned int& sp, unsigned int stride_bytes, int v) {
     asm volatile("st.shared.b32 [%0], %1;" :: "r"(sp), "r"(v) : "memory");
     sp += stride_bytes;
@@ -447,6 +454,16 @@ RT_DEV int stack_pop(unsigned int& sp, unsigned int stride_bytes) {
     int v;
     sp -= stride_bytes;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(sp) : "memory");
+    return v;
+}
+RT_DEV void stack_push2(unsigned int& sp, unsigned int stride_bytes, int v, int t) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" :: "r"(sp), "r"(v), "r"(t) : "memory");
+    sp += stride_bytes;
+}
+RT_DEV int stack_pop2(unsigned int& sp, unsigned int stride_bytes, int& t) {
+    int v;
+    sp -= stride_bytes;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "r"(sp) : "memory");
     return v;
 }
 
@@ -586,11 +603,24 @@ RT_DEV void trav_step(const BvhView& b, TravState& s, unsigned int stride, Trace
         const int n = __popc(pm);
 #pragma unroll
         for (int j = 3; j >= 1; --j) {
-            if (j < n) stack_push(sp, stride, first + (key[j] & 3));
+            if (j < n) {
+                if (RT_STACK_ENTRY_T) stack_push2(sp, stride, first + (key[j] & 3), key[j]);
+                else stack_push(sp, stride, first + (key[j] & 3));
+            }
         }
         if (n > 0) next = first + (key[0] & 3);
     }
-    if (next == RT_CUR_NONE && sp != s.sp0) next = stack_pop(sp, stride);
+    if (!ANY && RT_STACK_ENTRY_T) {
+        // drop popped sub-trees that start beyond the best hit (the key's low 2 bits are the slot:
+        // clearing them only lowers the entry bound for positive entries; negative ones always pass)
+        while (next == RT_CUR_NONE && sp != s.sp0) {
+            int key;
+            const int node2 = stack_pop2(sp, stride, key);
+            if (key < 0 || __int_as_float(key & ~3) <= s.lim) next = node2;
+        }
+    } else if (next == RT_CUR_NONE && sp != s.sp0) {
+        next = stack_pop(sp, stride);
+    }
     s.sp = sp;
     s.cur = next;
 }
