@@ -111,7 +111,9 @@ typedef struct rt_render_params {
     int32_t collect_stats; /* 1: also count node visits / primitive tests (slower) */
     int32_t reserved[7];   /* [0] bit 0: literal reference traversal (visit everything, exact tests only; validation)
                               [1] bit 0: record CUDA events around the trace/shadow/shade/light launches
-                                         (rt_scene_last_kernel_times) */
+                                         (rt_scene_last_kernel_times)
+                              [2] bit 0: serialise the launches of a frame on the caller's stream (by default the
+                                         shadow/light kernels of a level overlap the next level on a second stream) */
 } rt_render_params;
 
 typedef struct rt_render_stats {

@@ -42,7 +42,7 @@ class Stats:
 def make_params(use_bvh: bool = False, n_samples_sqrt: int = 4, light_samples: int = 1,
                 max_depth: int = MAX_RECURSION_DEPTH, seed: int = 1, fixed_time: float = -1.0, rank: int = 0,
                 world: int = 1, tile: Sequence[int] = (32, 32), collect_stats: bool = False,
-                prune: bool = True, time_kernels: bool = False) -> RenderParams:
+                prune: bool = True, time_kernels: bool = False, serial: bool = False) -> RenderParams:
     """Defaults are the reference binary's (raytracer.cpp:361-363: BVH off, 4x4 samples, 1 light sample)."""
     p = RenderParams()
     lib.rt_render_params_default(C.byref(p))
@@ -57,6 +57,7 @@ def make_params(use_bvh: bool = False, n_samples_sqrt: int = 4, light_samples: i
     p.collect_stats = int(bool(collect_stats))
     p.reserved[0] = 0 if prune else 1
     p.reserved[1] = 1 if time_kernels else 0
+    p.reserved[2] = 1 if serial else 0
     return p
 
 

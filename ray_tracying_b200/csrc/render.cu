@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -85,8 +86,9 @@ struct FrameParams {
     // wavefront buffers
     float4* q[2];                  // ray queues (ping-pong by level parity), 3 x float4 per ray
     int* hit_prim;                 // closest primitive per ray of the current level (-1 = miss)
-    float4* recs;                  // shade records, 5 x float4 per shaded hit
-    int* vis;                      // unoccluded shadow samples per (record, light)
+    float4* recs[2];               // shade records, 5 x float4 per shaded hit; by level parity, so that
+    int* vis[2];                   // shadow/light of level d can overlap trace/shade of level d+1
+                                   // (vis = unoccluded shadow samples per (record, light))
     unsigned long long* accum;     // 3 per pixel, fixed point 2^-40
     int* hit_ids;                  // optional frame-sized output
     unsigned int* lvl;             // [RT_MAX_DEPTH + 2][RT_LVL_STRIDE] per-level counters
@@ -355,13 +357,13 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
             float vx = r.ox - h.px, vy = r.oy - h.py, vz = r.oz - h.pz;  // view vector (raytracer.cpp:197)
             normalize3(vx, vy, vz);
             const float local_share = fmaxf(0.0f, 1.0f - reflectivity - transparency);  // raytracer.cpp:346
-            float4* o = p.recs + (size_t)rec * 5;
+            float4* o = p.recs[level & 1] + (size_t)rec * 5;
             o[0] = make_float4(h.px, h.py, h.pz, __uint_as_float(pixel));
             o[1] = make_float4(h.nx, h.ny, h.nz, weight * local_share);
             o[2] = make_float4(vx, vy, vz, __int_as_float(mat));
             o[3] = make_float4(br, bg, bb, 0.0f);
             o[4] = make_float4(__uint_as_float(sample), __uint_as_float(node), 0.0f, 0.0f);
-            for (int l = 0; l < p.n_lights; ++l) p.vis[(size_t)rec * p.n_lights + l] = 0;
+            for (int l = 0; l < p.n_lights; ++l) p.vis[level & 1][(size_t)rec * p.n_lights + l] = 0;
         }
 
         const bool deeper = level + 1 <= p.max_depth;
@@ -433,6 +435,8 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
 // ---------------------------------------------------------------------------------------------
 struct ShadowRays {
     const FrameParams& p;
+    const float4* __restrict__ recs;  // this level's shade records
+    int* vis;
     unsigned int n_recs;
     int* vis_slot;
     RT_DEV void load(long long item, Ray& sr, float& max_t) {
@@ -450,11 +454,11 @@ struct ShadowRays {
         }
         const unsigned int rec = (unsigned int)(rest / (unsigned int)cnt);
         const int k = (int)(rest % (unsigned int)cnt);
-        const float4 r0 = p.recs[(size_t)rec * 5 + 0], r1 = p.recs[(size_t)rec * 5 + 1];
+        const float4 r0 = recs[(size_t)rec * 5 + 0], r1 = recs[(size_t)rec * 5 + 1];
         float tx = l0.x, ty = l0.y, tz = l0.z;
         const float radius = l1.w;
         if (radius > 0.0f) {
-            const float4 r4 = p.recs[(size_t)rec * 5 + 4];
+            const float4 r4 = recs[(size_t)rec * 5 + 4];
             RngCtx g = {__float_as_uint(r0.w), p.seed_lo, p.seed_hi, __float_as_uint(r4.x)};
             float rx, ry, rz;
             random_in_unit_sphere(g, RNG_LIGHT, __float_as_uint(r4.y), ((uint32_t)li << 16) | (uint32_t)k, rx, ry, rz);
@@ -466,7 +470,7 @@ struct ShadowRays {
         sr.ox = r0.x + r1.x * 1e-4f; sr.oy = r0.y + r1.y * 1e-4f; sr.oz = r0.z + r1.z * 1e-4f;
         sr.dx = lx; sr.dy = ly; sr.dz = lz;
         sr.time = 0.0f;  // `Ray shadowRay;` keeps the default time (shapes.hpp:28)
-        vis_slot = p.vis + (size_t)rec * p.n_lights + li;
+        vis_slot = vis + (size_t)rec * p.n_lights + li;
     }
     // nothing closer than the light: this sample is lit (raytracer.cpp:233-235)
     RT_DEV void store(long long, const TravState& s) const { if (s.best_prim < 0) atomicAdd(vis_slot, 1); }
@@ -477,7 +481,7 @@ __global__ void __launch_bounds__(RT_TRACE_THREADS, RT_TRACE_MINBLOCKS) shadow_k
     unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
     const unsigned long long n = (unsigned long long)lv[L_RECS] * (unsigned long long)p.shadow_per_rec;
     TraceStats st = {0u, 0u};
-    ShadowRays src = {p, lv[L_RECS], nullptr};
+    ShadowRays src = {p, p.recs[level & 1], p.vis[level & 1], lv[L_RECS], nullptr};
     wave_loop<true, STATS>(p.bvh, src, lv + L_WORK_SHADOW, n, st);
     if (STATS) flush_stats(p, st);
 }
@@ -489,7 +493,7 @@ __global__ void __launch_bounds__(RT_TRACE_THREADS, RT_TRACE_MINBLOCKS) shadow_k
 __global__ void __launch_bounds__(256) light_kernel(const __grid_constant__ FrameParams p, int level) {
     const unsigned int n = p.lvl[level * RT_LVL_STRIDE + L_RECS];
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4* rc = p.recs + (size_t)i * 5;
+        const float4* rc = p.recs[level & 1] + (size_t)i * 5;
         const float4 r0 = rc[0], r1 = rc[1], r2 = rc[2], r3 = rc[3];
         const int mat = __float_as_int(r2.w);
         const float4 m0 = __ldg(p.mats + 4 * mat + 0);
@@ -503,7 +507,7 @@ __global__ void __launch_bounds__(256) light_kernel(const __grid_constant__ Fram
             const float4 l1 = __ldg(p.lights + 2 * li + 1);
             const int shadow_samples = (l1.w > 0.0f) ? p.light_samples : 1;
             // visibility += 1.0f per unoccluded sample, then /= samples: the count is exact in float
-            float visibility = (float)p.vis[(size_t)i * p.n_lights + li];
+            float visibility = (float)p.vis[level & 1][(size_t)i * p.n_lights + li];
             visibility /= (float)shadow_samples;
             if (visibility <= 0.0f) continue;
             float cx = l0.x - r0.x, cy = l0.y - r0.y, cz = l0.z - r0.z;
@@ -601,8 +605,10 @@ struct DeviceScene {
     // wavefront buffers
     float4* q[2] = {nullptr, nullptr};
     int* hit_prim = nullptr;
-    float4* recs = nullptr;
-    int* vis = nullptr;
+    float4* recs[2] = {nullptr, nullptr};
+    int* vis[2] = {nullptr, nullptr};
+    cudaStream_t aux = nullptr;                  // shadow + light kernels run here, overlapping the next level
+    std::vector<cudaEvent_t> ev_shade, ev_light;  // per level
     long long capacity = 0;
     int vis_lights = 0;
     unsigned long long* accum = nullptr;
@@ -641,7 +647,11 @@ static void free_device(DeviceScene* d) {
     if (!d) return;
     cudaFree(d->arena);
     if (d->staging) cudaFreeHost(d->staging);
-    cudaFree(d->q[0]); cudaFree(d->q[1]); cudaFree(d->hit_prim); cudaFree(d->recs); cudaFree(d->vis);
+    cudaFree(d->q[0]); cudaFree(d->q[1]); cudaFree(d->hit_prim);
+    for (int i = 0; i < 2; ++i) { cudaFree(d->recs[i]); cudaFree(d->vis[i]); }
+    if (d->aux) cudaStreamDestroy(d->aux);
+    for (cudaEvent_t e : d->ev_shade) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : d->ev_light) if (e) cudaEventDestroy(e);
     cudaFree(d->accum); cudaFree(d->lvl); cudaFree(d->totals);
     cudaFree(d->out_rgb); cudaFree(d->out_ids); cudaFree(d->out_lin);
     for (cudaEvent_t e : d->ev) if (e) cudaEventDestroy(e);
@@ -802,14 +812,17 @@ static int ensure_buffers(DeviceScene* d, const FrameParams& k, long long batch_
     if (want_cap > d->capacity || k.n_lights > d->vis_lights) {
         const long long cap = std::max(want_cap, d->capacity);
         const int nl = std::max(1, std::max(k.n_lights, d->vis_lights));
-        cudaFree(d->q[0]); cudaFree(d->q[1]); cudaFree(d->hit_prim); cudaFree(d->recs); cudaFree(d->vis);
-        d->q[0] = d->q[1] = nullptr; d->hit_prim = nullptr; d->recs = nullptr; d->vis = nullptr;
+        cudaFree(d->q[0]); cudaFree(d->q[1]); cudaFree(d->hit_prim);
+        d->q[0] = d->q[1] = nullptr; d->hit_prim = nullptr;
+        for (int i = 0; i < 2; ++i) { cudaFree(d->recs[i]); cudaFree(d->vis[i]); d->recs[i] = nullptr; d->vis[i] = nullptr; }
         d->capacity = 0;
         CUDA_TRY(cudaMalloc((void**)&d->q[0], (size_t)cap * 3 * sizeof(float4)));
         CUDA_TRY(cudaMalloc((void**)&d->q[1], (size_t)cap * 3 * sizeof(float4)));
         CUDA_TRY(cudaMalloc((void**)&d->hit_prim, (size_t)cap * sizeof(int)));
-        CUDA_TRY(cudaMalloc((void**)&d->recs, (size_t)cap * 5 * sizeof(float4)));
-        CUDA_TRY(cudaMalloc((void**)&d->vis, (size_t)cap * nl * sizeof(int)));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaMalloc((void**)&d->recs[i], (size_t)cap * 5 * sizeof(float4)));
+            CUDA_TRY(cudaMalloc((void**)&d->vis[i], (size_t)cap * nl * sizeof(int)));
+        }
         d->capacity = cap;
         d->vis_lights = nl;
     }
@@ -825,13 +838,15 @@ static int ensure_buffers(DeviceScene* d, const FrameParams& k, long long batch_
 }
 
 // Enqueues one frame on `stream` (no host synchronisation).
-static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time_classes, uint8_t* rgb8, float* linear, cudaStream_t stream) {
+static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time_classes, bool serial, uint8_t* rgb8, float* linear,
+                         cudaStream_t stream) {
     const long long total_units = (long long)k.n_my_tiles * k.sub_per_tile * k.spp;  // unit = 32 (pixel, sample) slots
     const long long batch_units = std::max<long long>(1, std::min<long long>(std::max<long long>(total_units, 1), d->batch_slots / 32));
     int rc = ensure_buffers(d, k, batch_units * 32);
     if (rc != RT_OK) return rc;
     k.q[0] = d->q[0]; k.q[1] = d->q[1];
-    k.hit_prim = d->hit_prim; k.recs = d->recs; k.vis = d->vis;
+    k.hit_prim = d->hit_prim;
+    for (int i = 0; i < 2; ++i) { k.recs[i] = d->recs[i]; k.vis[i] = d->vis[i]; }
     k.accum = d->accum; k.lvl = d->lvl; k.totals = d->totals;
     k.capacity = (int)std::min<long long>(d->capacity, wanted_capacity(batch_units * 32));
 
@@ -848,17 +863,35 @@ static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time
         d->class_ev.resize(2 * max_pairs, nullptr);
         for (size_t i = have; i < d->class_ev.size(); ++i) CUDA_TRY(cudaEventCreate(&d->class_ev[i]));
     }
-    auto mark = [&](int cls, bool begin) {  // event before / after a launch of class cls
-        if (!time_classes) return;
-        if (begin) {
-            if (d->class_of.size() >= max_pairs) return;
-            cudaEventRecord(d->class_ev[2 * d->class_of.size()], stream);
-            d->class_of.push_back(cls | 0x100);  // 0x100: waiting for its end event
-        } else if (!d->class_of.empty() && (d->class_of.back() & 0x100)) {
-            cudaEventRecord(d->class_ev[2 * (d->class_of.size() - 1) + 1], stream);
-            d->class_of.back() &= 0xff;
-        }
+    // returns the pair index (or -1) at the begin mark; the end mark takes it back
+    auto mark_begin = [&](int cls, cudaStream_t on) -> int {
+        if (!time_classes || d->class_of.size() >= max_pairs) return -1;
+        const int pair = (int)d->class_of.size();
+        cudaEventRecord(d->class_ev[2 * pair], on);
+        d->class_of.push_back(cls | 0x100);  // 0x100: waiting for its end event
+        return pair;
     };
+    auto mark_end = [&](int pair, cudaStream_t on) {
+        if (pair < 0) return;
+        cudaEventRecord(d->class_ev[2 * pair + 1], on);
+        d->class_of[pair] &= 0xff;
+    };
+    // Two streams: trace + shade of level d+1 (main) overlap shadow + light of level d (aux) -- both
+    // pairs only depend on shade(d). The persistent kernels fill the GPU, so the overlap mostly
+    // hides each kernel's tail behind the other's start. RT_B200_OVERLAP=0 serialises everything.
+    static const bool overlap_enabled = [] { const char* e = std::getenv("RT_B200_OVERLAP"); return !(e && e[0] == '0'); }();
+    const bool overlap = overlap_enabled && !serial;
+    if (overlap && !d->aux) CUDA_TRY(cudaStreamCreateWithFlags(&d->aux, cudaStreamNonBlocking));
+    const cudaStream_t aux = overlap ? d->aux : stream;
+    if (d->ev_shade.size() < RT_MAX_DEPTH + 2) {
+        const size_t have = d->ev_shade.size();
+        d->ev_shade.resize(RT_MAX_DEPTH + 2, nullptr);
+        d->ev_light.resize(RT_MAX_DEPTH + 2, nullptr);
+        for (size_t i = have; i < d->ev_shade.size(); ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&d->ev_shade[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&d->ev_light[i], cudaEventDisableTiming));
+        }
+    }
     const int grid_trace = d->sm_count * d->trace_blocks;
     const int grid_shadow = d->sm_count * d->shadow_blocks;
     const int grid_wide = d->sm_count * 8;
@@ -867,25 +900,34 @@ static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time
         gen_kernel<<<std::min(grid_wide, (n_units + 7) / 8), 256, 0, stream>>>(k, u0, n_units);
         ++launches;
         for (int level = 0; level <= k.max_depth; ++level) {
-            mark(0, true);
+            int pr = mark_begin(0, stream);
             if (collect) trace_kernel<true><<<grid_trace, RT_TRACE_THREADS, d->stack_bytes, stream>>>(k, level);
             else trace_kernel<false><<<grid_trace, RT_TRACE_THREADS, d->stack_bytes, stream>>>(k, level);
-            mark(0, false);
-            mark(2, true);
+            mark_end(pr, stream);
+            // shade(level) overwrites the record buffers that shadow/light of level - 2 read
+            if (aux != stream && level >= 2) CUDA_TRY(cudaStreamWaitEvent(stream, d->ev_light[level - 2], 0));
+            pr = mark_begin(2, stream);
             shade_kernel<<<grid_wide, 256, 0, stream>>>(k, level);
-            mark(2, false);
+            mark_end(pr, stream);
+            if (aux != stream) {
+                CUDA_TRY(cudaEventRecord(d->ev_shade[level], stream));
+                CUDA_TRY(cudaStreamWaitEvent(aux, d->ev_shade[level], 0));
+            }
             if (k.shadow_per_rec > 0) {
-                mark(1, true);
-                if (collect) shadow_kernel<true><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, stream>>>(k, level);
-                else shadow_kernel<false><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, stream>>>(k, level);
-                mark(1, false);
+                pr = mark_begin(1, aux);
+                if (collect) shadow_kernel<true><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, aux>>>(k, level);
+                else shadow_kernel<false><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, aux>>>(k, level);
+                mark_end(pr, aux);
                 ++launches;
             }
-            mark(3, true);
-            light_kernel<<<grid_wide, 256, 0, stream>>>(k, level);
-            mark(3, false);
+            pr = mark_begin(3, aux);
+            light_kernel<<<grid_wide, 256, 0, aux>>>(k, level);
+            mark_end(pr, aux);
+            if (aux != stream) CUDA_TRY(cudaEventRecord(d->ev_light[level], aux));
             launches += 3;
         }
+        // aux is ordered: the last light kernel finishes after all earlier ones
+        if (aux != stream) CUDA_TRY(cudaStreamWaitEvent(stream, d->ev_light[k.max_depth], 0));
         fold_kernel<<<1, 32, 0, stream>>>(k);
         ++launches;
     }
@@ -910,7 +952,7 @@ static int render_impl(HostScene& h, const rt_render_params& rp, uint8_t* rgb8, 
     for (int attempt = 0;; ++attempt) {
         CUDA_TRY(cudaEventRecord(d->ev[0], stream));
         CUDA_TRY(cudaEventRecord(d->ev[1], stream));
-        if ((rc = enqueue_frame(d, k, rp.collect_stats != 0, (rp.reserved[1] & 1) != 0, rgb8, linear, stream)) != RT_OK) return rc;
+        if ((rc = enqueue_frame(d, k, rp.collect_stats != 0, (rp.reserved[1] & 1) != 0, (rp.reserved[2] & 1) != 0, rgb8, linear, stream)) != RT_OK) return rc;
         CUDA_TRY(cudaEventRecord(d->ev[2], stream));
         d->timed = true;
         if (!stats) return RT_OK;  // asynchronous: an overflow would be reported by the next synchronous call

@@ -38,12 +38,39 @@ def max_rank_pixels(width: int, height: int, tile: Tuple[int, int], world: int) 
     return int(np.bincount(owner, minlength=world).max())
 
 
+_PLAN_CACHE: dict = {}
+
+
+def _gather_plan(width: int, height: int, tile: Tuple[int, int], world: int, rank: int, device):
+    """Index tensors of the frame-end exchange, built once per (frame geometry, world, device):
+    `mine` = this rank's pixels (for packing), `scatter` = for every slot of the gathered
+    (world x cap) buffer the flat pixel it belongs to (padding slots point at a scratch pixel)."""
+    import torch
+
+    key = (width, height, tuple(tile), world, rank, str(device))
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        owner = tile_owner(width, height, tile, world).reshape(-1)
+        cap = int(np.bincount(owner, minlength=world).max())
+        scatter = np.full((world, cap), width * height, dtype=np.int64)  # scratch slot = one past the frame
+        mine = None
+        for r in range(world):
+            idx = np.flatnonzero(owner == r).astype(np.int64)
+            scatter[r, : idx.size] = idx
+            if r == rank:
+                mine = idx
+        plan = (torch.from_numpy(mine).to(device), torch.from_numpy(scatter.reshape(-1)).to(device), cap)
+        _PLAN_CACHE[key] = plan
+    return plan
+
+
 def gather_frame(local_frame, width: int, height: int, tile: Tuple[int, int], rank: int, world: int, group=None):
     """Assembles the full frame on every rank.
 
     local_frame: torch tensor (H, W, C) on this rank's device in which only this rank's tiles are
-    valid. Each rank packs its own pixels, one all_gather moves world x max_rank_pixels x C
-    elements, and every rank scatters the pieces into a full (H, W, C) tensor.
+    valid. Each rank packs its own pixels (one gather kernel), ONE all_gather moves
+    world x max_rank_pixels x C elements over NCCL / NVLink, and one scatter kernel writes the
+    pieces into a full (H, W, C) tensor. The index tensors are cached per frame geometry.
     """
     import torch
     import torch.distributed as dist
@@ -53,14 +80,11 @@ def gather_frame(local_frame, width: int, height: int, tile: Tuple[int, int], ra
     c = local_frame.shape[-1]
     dev = local_frame.device
     flat = local_frame.reshape(-1, c)
-    cap = max_rank_pixels(width, height, tile, world)
-    mine = torch.from_numpy(rank_pixel_indices(width, height, tile, world, rank)).to(dev)
+    mine, scatter, cap = _gather_plan(width, height, tile, world, rank, dev)
     packed = torch.zeros((cap, c), dtype=local_frame.dtype, device=dev)
     packed[: mine.numel()] = flat.index_select(0, mine)
-    gathered = torch.empty((world, cap, c), dtype=local_frame.dtype, device=dev)
-    dist.all_gather_into_tensor(gathered.view(-1, c), packed, group=group)
-    out = torch.empty_like(flat)
-    for r in range(world):
-        idx = mine if r == rank else torch.from_numpy(rank_pixel_indices(width, height, tile, world, r)).to(dev)
-        out.index_copy_(0, idx, gathered[r, : idx.numel()])
-    return out.reshape(height, width, c)
+    gathered = torch.empty((world * cap, c), dtype=local_frame.dtype, device=dev)
+    dist.all_gather_into_tensor(gathered, packed, group=group)
+    out = torch.empty((width * height + 1, c), dtype=local_frame.dtype, device=dev)  # + scratch pixel
+    out.index_copy_(0, scatter, gathered)
+    return out[: width * height].reshape(height, width, c)
