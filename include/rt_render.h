@@ -185,8 +185,9 @@ int rt_scene_last_timing(rt_scene* scene, float* kernel_ms, float* total_ms);
 
 /* Per-kernel-class CUDA-event times of the most recent frame rendered with reserved[1] bit 0 set:
  * ms4 / launches4 = {trace_kernel, shadow_kernel, shade_kernel, light_kernel} (sum of the launch
- * durations, number of launches). Events are recorded on the launching stream; waits for them. */
-int rt_scene_last_kernel_times(rt_scene* scene, float* ms4, int32_t* launches4);
+ * durations, number of TIMED launches -- at most 512 per frame); frame_launches4 = all launches of
+ * the frame per class. Events are recorded on the launching stream; waits for them. */
+int rt_scene_last_kernel_times(rt_scene* scene, float* ms4, int32_t* launches4, int32_t* frame_launches4);
 
 /* Number of pixels this rank renders for (rank, world, tile). */
 int rt_shard_pixels(const rt_scene* scene, const rt_render_params* p, int64_t* n_pixels);

@@ -179,10 +179,11 @@ class Scene:
         return k.value, t.value
 
     def last_kernel_times(self) -> dict:
-        """{class: (ms, launches)} of the most recent frame rendered with time_kernels=True."""
-        ms, n = (C.c_float * 4)(), (C.c_int32 * 4)()
-        check(lib.rt_scene_last_kernel_times(self._h, ms, n), "rt_scene_last_kernel_times")
-        return {k: (ms[i], n[i]) for i, k in enumerate(("trace", "shadow", "shade", "light"))}
+        """{class: (ms, timed launches, launches of the frame)} of the most recent frame rendered with
+        time_kernels=True (at most 512 launches of a frame are timed)."""
+        ms, n, tot = (C.c_float * 4)(), (C.c_int32 * 4)(), (C.c_int32 * 4)()
+        check(lib.rt_scene_last_kernel_times(self._h, ms, n, tot), "rt_scene_last_kernel_times")
+        return {k: (ms[i], n[i], tot[i]) for i, k in enumerate(("trace", "shadow", "shade", "light"))}
 
     def shard_pixels(self, params: RenderParams) -> int:
         n = C.c_int64()

@@ -627,6 +627,7 @@ struct DeviceScene {
     // trace / shadow / shade / light launches of the most recent frame
     std::vector<cudaEvent_t> class_ev;
     std::vector<int> class_of;  // class of pair i: 0 trace, 1 shadow, 2 shade, 3 light
+    int class_launches[4] = {0, 0, 0, 0};  // all launches of the frame per class (timed or not)
     // frame-sized device outputs of rt_render (host-buffer entry point), kept between calls
     uint8_t* out_rgb = nullptr;
     int32_t* out_ids = nullptr;
@@ -864,7 +865,9 @@ static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time
         for (size_t i = have; i < d->class_ev.size(); ++i) CUDA_TRY(cudaEventCreate(&d->class_ev[i]));
     }
     // returns the pair index (or -1) at the begin mark; the end mark takes it back
+    for (int& c : d->class_launches) c = 0;
     auto mark_begin = [&](int cls, cudaStream_t on) -> int {
+        d->class_launches[cls]++;
         if (!time_classes || d->class_of.size() >= max_pairs) return -1;
         const int pair = (int)d->class_of.size();
         cudaEventRecord(d->class_ev[2 * pair], on);
@@ -1076,7 +1079,7 @@ int rt_scene_last_timing(rt_scene* scene, float* kernel_ms, float* total_ms) {
     return RT_OK;
 }
 
-int rt_scene_last_kernel_times(rt_scene* scene, float* ms4, int32_t* launches4) {
+int rt_scene_last_kernel_times(rt_scene* scene, float* ms4, int32_t* launches4, int32_t* frame_launches4) {
     if (!scene) { rtb::set_error("null scene"); return RT_ERR_INVALID; }
     rtb::DeviceScene* d = rtb::host_of(scene)->dev;
     if (!d || !d->timed) { rtb::set_error("rt_scene_last_kernel_times: no render has been recorded on this scene"); return RT_ERR_INVALID; }
@@ -1091,7 +1094,11 @@ int rt_scene_last_kernel_times(rt_scene* scene, float* ms4, int32_t* launches4) 
         n[d->class_of[i] & 3] += 1;
     }
     if (e != cudaSuccess) { rtb::set_error(std::string("rt_scene_last_kernel_times: ") + cudaGetErrorString(e)); return RT_ERR_CUDA; }
-    for (int i = 0; i < 4; ++i) { if (ms4) ms4[i] = ms[i]; if (launches4) launches4[i] = n[i]; }
+    for (int i = 0; i < 4; ++i) {
+        if (ms4) ms4[i] = ms[i];
+        if (launches4) launches4[i] = n[i];
+        if (frame_launches4) frame_launches4[i] = d->class_launches[i];
+    }
     return RT_OK;
 }
 

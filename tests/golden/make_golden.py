@@ -54,9 +54,58 @@ def stochastic(name, scene, s=64, light_samples=1, depth=10, seed=7):
     print(name, "spp", s * s, "seconds", info.get("seconds"))
 
 
+def numerics_edge_scene():
+    """Cases that stress the fast traversal's exactness machinery: an axis-aligned camera with an ODD
+    width (the centre column has d.x == 0 exactly -> the reference's 'parallel' rule, and its
+    neighbours have |d.x| just above 1e-6), a light exactly above the origin (vertical shadow rays),
+    degenerate quads (repeated corner: the reference's inside test accepts a whole line), a non-planar
+    quad, sub-pixel and strongly anisotropic spheres (discriminant cancellation), axis-aligned cubes
+    (box == shape) and glass / mirror materials so that secondary rays start on all of them."""
+    sc = scenes.mixed_scene(0, seed=2, resolution=(161, 91), extent=6.0, height=1.0, fractions=(1, 0, 0, 0))
+    sc["cameras"] = [scenes.camera_block((0.0, -9.0, 1.5), (0.0, 0.0, 1.5), focal_length=30.0)]
+    sc["lights"] = [{"location": [0.0, 0.0, 6.0], "intensity": 900.0, "color": [1.0, 1.0, 1.0], "radius": 0.0},
+                    {"location": [4.0, -5.0, 3.0], "intensity": 700.0, "color": [1.0, 0.9, 0.8], "radius": 0.0}]
+    m = scenes.material_block
+    glass = m(diffuse=(0.95, 0.95, 1.0), roughness=0.0, reflectivity=0.1, transparency=0.8, refractive_index=1.5)
+    mirror = m(diffuse=(0.9, 0.9, 0.9), roughness=0.0, reflectivity=0.6)
+    red, green, blue = m(diffuse=(0.9, 0.2, 0.2)), m(diffuse=(0.2, 0.9, 0.2)), m(diffuse=(0.2, 0.3, 0.9))
+    sc["rectangles"] = [
+        {"translation": [0.0, 0.0, 0.0], "rotation": [0.0, 0.0, 0.0], "scale": [30.0, 30.0, 1.0], "material": mirror},
+        {"translation": [0.0, 3.0, 1.5], "rotation": [1.5707963, 0.0, 0.0], "scale": [2.0, 1.0, 1.0], "material": blue},
+    ]
+    sc["spheres"] = [
+        {"location": [0.0, 0.0, 1.5], "rotation": [0.0, 0.0, 0.0], "scale": [1.0, 1.0, 1.0], "material": glass},
+        {"location": [0.3, 40.0, 3.0], "rotation": [0.0, 0.0, 0.0], "scale": [0.004, 0.004, 0.004], "material": red},
+        {"location": [-0.8, 35.0, 2.0], "rotation": [0.3, 0.2, 0.1], "scale": [0.02, 0.02, 0.02], "material": red},
+        {"location": [2.5, 1.0, 1.0], "rotation": [0.4, 0.9, 0.2], "scale": [1.2, 0.9, 0.01], "material": green},
+        {"location": [-2.5, 0.5, 0.8], "rotation": [0.0, 0.0, 0.0], "scale": [0.03, 0.8, 0.8], "material": mirror},
+        {"location": [-4.0, 2.0, 2.5], "rotation": [0.0, 0.0, 0.0], "scale": [0.5, 0.5, 0.5], "material": blue},
+    ]
+    sc["cubes"] = [
+        {"translation": [0.0, 5.0, 1.0], "rotation": [0.0, 0.0, 0.0], "scale": [2.0, 2.0, 2.0], "material": mirror},
+        {"translation": [3.0, -2.0, 0.5], "rotation": [0.0, 0.0, 0.0], "scale": [1.0, 1.0, 1.0], "material": green},
+        {"translation": [-3.0, -3.0, 0.25], "rotation": [0.0, 0.0, 0.7853982], "scale": [0.5, 3.0, 0.5], "material": red},
+        {"translation": [1.2, -4.0, 1.5], "rotation": [0.5, 0.3, 0.1], "scale": [0.02, 0.6, 0.6], "material": glass},
+    ]
+    sc["planes"] = [
+        # proper quad, triangle with a repeated corner (c3 == c2), one with c1 == c0 (no valid normal)
+        {"corners": [[-5, 6, 0.5], [-3, 6, 0.5], [-5, 6, 2.5], [-3, 6, 2.5]], "material": green},
+        {"corners": [[3, 6, 0.5], [5, 6, 0.5], [4, 6, 2.5], [4, 6, 2.5]], "material": red},
+        {"corners": [[1, 2, 3], [1, 2, 3], [2, 2, 3], [2, 3, 3]], "material": red},
+        # non-planar quad (corner 3 lifted off the plane of corners 0..2), sliver triangle
+        {"corners": [[-1.5, -2, 0.2], [-0.5, -2, 0.2], [-1.5, -1, 0.2], [-0.5, -1, 0.9]], "material": blue},
+        {"corners": [[1.5, -3, 0.3], [3.5, -3, 0.3], [2.5, -2.999, 0.3], [2.5, -2.999, 0.3]], "material": blue},
+        {"corners": [[-6, -1, 0.1], [-5.9999, -1, 0.1], [-6, 1, 2.0], [-5.9999, 1, 2.0]], "material": green},
+    ]
+    return sc
+
+
 def main():
     if not RefDriver.available():
         raise SystemExit("oracle/_ref/ref_driver missing: run `make -C oracle ref` first")
+    if len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "numerics_edge":
+        deterministic("numerics_edge", numerics_edge_scene(), depth=4)
+        return
 
     # (0) the reference's own scene (ASCII/scene.json), minified; glossy, so only IDs/t are deterministic
     with open("/root/reference/ASCII/scene.json") as f:
@@ -102,6 +151,7 @@ def main():
         {"corners": [[-3, -1, 3], [-2, -1, 3], [-3, -1, 3], [-2, -1, 3]]},
     ]
     deterministic("ties_axis_aligned", tie)
+    deterministic("numerics_edge", numerics_edge_scene(), depth=4)
 
     # (3) textures: the reference resolves "x.jpg" to ../../Textures/x.ppm relative to its cwd
     tmp = tempfile.mkdtemp()

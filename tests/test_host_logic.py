@@ -43,7 +43,7 @@ def test_defaults_are_the_reference_cli_defaults(rt):
     assert (p.rank, p.world) == (0, 1)
 
 
-@pytest.mark.parametrize("name", ["mixed_400", "few_3", "few_5", "ties_axis_aligned", "textured_40", "empty"])
+@pytest.mark.parametrize("name", ["mixed_400", "few_3", "few_5", "ties_axis_aligned", "numerics_edge", "textured_40", "empty"])
 def test_bvh_equals_reference_tree(rt, name):
     """Tree topology, leaf contents and every box bit-equal to the reference's (golden dump)."""
     scene = rt.Scene.from_json(os.path.join(GOLDEN, name + ".json"), GOLDEN)

@@ -13,7 +13,7 @@ import pytest
 
 from conftest import GOLDEN, golden_data, golden_scene, rmse, scene_file, with_resolution
 
-DETERMINISTIC = ["mixed_400", "mixed_400_depth5", "few_3", "few_5", "ties_axis_aligned", "textured_40", "empty"]
+DETERMINISTIC = ["mixed_400", "mixed_400_depth5", "few_3", "few_5", "ties_axis_aligned", "numerics_edge", "textured_40", "empty"]
 STOCHASTIC = ["soft_shadows", "glossy", "dof", "motion_blur", "antialias"]
 
 
