@@ -61,7 +61,11 @@ namespace rtb {
 #ifndef RT_STEPS_PER_VOTE
 #define RT_STEPS_PER_VOTE 3
 #endif
-enum LevelCounter { L_RAYS = 0, L_RECS = 1, L_WORK_TRACE = 2, L_WORK_SHADOW = 3 };
+// L_RAYS / L_RECS are queue SIZES (level 0 is not compacted: slot = packet * 32 + lane, with dead
+// slots, so that a packet of 32 consecutive slots is one 8x4 pixel block); L_LIVE_* count the real
+// rays / shade records for the statistics.
+enum LevelCounter { L_RAYS = 0, L_RECS = 1, L_WORK_TRACE = 2, L_WORK_SHADOW = 3, L_LIVE_RAYS = 4, L_LIVE_RECS = 5 };
+#define RT_DEAD 0xffffffffu  /* pixel field of a dead ray slot / invalid shade record */
 enum Total { T_PRIMARY = 0, T_SHADOW = 1, T_SECONDARY = 2, T_NODES = 3, T_PRIMS = 4, T_OVERFLOW = 5 };
 
 struct FrameParams {
@@ -139,8 +143,21 @@ __global__ void __launch_bounds__(256) gen_kernel(const __grid_constant__ FrameP
         const int lx = (sub % p.sub_x) * 8 + (lane & 7), ly = (sub / p.sub_x) * 4 + (lane >> 3);
         const int x = (tile % p.tiles_x) * p.tile_w + lx, y = (tile / p.tiles_x) * p.tile_h + ly;
         const bool valid = lx < p.tile_w && ly < p.tile_h && x < p.res_x && y < p.res_y;
-        const unsigned int slot = warp_reserve(p.lvl + L_RAYS, valid);
-        if (!valid) continue;
+        const unsigned int slot = (unsigned int)w * 32u + (unsigned int)lane;  // one packet per unit, no compaction
+        {
+            const unsigned int live = __ballot_sync(0xffffffffu, valid);
+            if (lane == 0) {
+                if (live) atomicAdd(p.lvl + L_LIVE_RAYS, (unsigned int)__popc(live));
+                if (w == 0) p.lvl[L_RAYS] = (unsigned int)n_units * 32u;
+            }
+        }
+        if (!valid) {  // dead slot: zero direction, pixel = RT_DEAD
+            float4* q = p.q[0] + (size_t)slot * 3;
+            q[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            q[1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            q[2] = make_float4(__uint_as_float(RT_DEAD), 0.0f, 0.0f, 0.0f);
+            continue;
+        }
         const uint32_t pixel = (uint32_t)(y * p.res_x + x);
         const U4 u = rt_rng(pixel, p.seed_lo, p.seed_hi, (uint32_t)s, RNG_CAMERA, 0u, 0u, 0u);
         float fx, fy;
@@ -230,8 +247,8 @@ RT_DEV void wave_loop(const BvhView& bvh, Src& src, unsigned int* counter, unsig
                     item = got;
                     Ray r;
                     float max_t;
-                    src.load(item, r, max_t);
-                    if (trav_begin<ANY>(bvh, s, r, max_t, st)) { src.store(item, s); item = -1; }
+                    if (!src.load(item, r, max_t)) item = -1;
+                    else if (trav_begin<ANY>(bvh, s, r, max_t, st)) { src.store(item, s); item = -1; }
                 }
                 continue;
             }
@@ -250,6 +267,147 @@ RT_DEV void wave_loop(const BvhView& bvh, Src& src, unsigned int* counter, unsig
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// packet_loop: traversal for COHERENT waves (the view rays of an 8x4 pixel block, and the shadow
+// rays of its hit points towards one light). The 32 rays of a warp share ONE traversal: one
+// stack (per warp, in shared memory), one node per step -- the node load is a broadcast, the
+// stack and the order are warp-uniform, and at a leaf all lanes test the SAME primitive, so the
+// intersection routine runs converged whatever the mix of primitive types in the scene.
+// Every stack entry carries the mask of lanes that passed the child's box (and, for a gated
+// child, the reference's leaf test), so each lane visits exactly the nodes its own per-ray
+// traversal could visit and tests a primitive only if its own culling box and its own leaf gate
+// passed: per lane the result is the same (t, shape) as wave_loop's. Lanes outside the mask idle;
+// the packet pays off while the rays stay together (measured: see profiles/README.md).
+// Stack entry = (node, lane mask, key): key = smallest entry parameter among the lanes (closest
+// hit only): a popped sub-tree is dropped for lanes whose best hit is nearer.
+// ---------------------------------------------------------------------------------------------
+template <bool ANY, bool STATS, class Src>
+RT_DEV void packet_loop(const BvhView& bvh, Src& src, unsigned int* counter, unsigned long long n, TraceStats& st) {
+    const unsigned int FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    // per-warp stack of 16-byte entries (node, lane mask, key, -): one STS.128 / one broadcast LDS.128
+    const unsigned int stk0 = (unsigned int)__cvta_generic_to_shared(rt_stack_smem) + (threadIdx.x >> 5) * bvh.stack_depth * 16u;
+    TravState s;
+    s.sp0 = 0u;
+    s.imax = 0.0f;
+    while (true) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(counter, 32u);
+        base = __shfl_sync(FULL, base, 0);
+        if ((unsigned long long)base >= n) break;
+        const long long item = (long long)base + lane;
+        bool active = (unsigned long long)item < n;
+        if (active) {
+            Ray r;
+            float max_t;
+            if (!src.load(item, r, max_t)) active = false;
+            else if (trav_begin<ANY>(bvh, s, r, max_t, st)) { src.store(item, s); active = false; }
+        }
+        const bool traversing = active;
+        unsigned int alive = __ballot_sync(FULL, active);  // lanes still looking for an answer
+        unsigned int sp = stk0;
+        int cur = 0;
+        unsigned int curmask = alive;
+        while (alive != 0u) {
+            // ---- visit node `cur` with the lanes of curmask ----
+            const float* w = bvh.wide + (size_t)cur * 32;
+            const F8 X = ldg256(w), Y = ldg256(w + 8), Z = ldg256(w + 16), C = ldg256(w + 24);
+            const bool in = (curmask >> lane) & 1u;
+            if (STATS && in) st.nodes += 4;
+            const int first = __float_as_int(C.v[0]);
+            const unsigned int meta = __float_as_uint(C.v[1]);
+            const float qi = C.v[2] * s.imax;
+            bool pass[4], sure[4];
+            float ent[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                wide_child_test(s, X.v[k], X.v[4 + k], Y.v[k], Y.v[4 + k], Z.v[k], Z.v[4 + k], qi, pass[k], sure[k], ent[k]);
+            unsigned int pm = ((pass[0] ? 1u : 0u) | (pass[1] ? 2u : 0u) | (pass[2] ? 4u : 0u) | (pass[3] ? 8u : 0u)) & meta;
+            if (!in) pm = 0u;
+            const unsigned int sm = (sure[0] ? 1u : 0u) | (sure[1] ? 2u : 0u) | (sure[2] ? 4u : 0u) | (sure[3] ? 8u : 0u);
+            unsigned int ex = pm & ~sm & (meta >> 4);
+            while (ex != 0u) {  // gated children too close to call: the reference's exact test (rare)
+                const int k = __ffs(ex) - 1;
+                ex &= ex - 1u;
+                const float* c = w + k;
+                if (!box_exact_call(__ldg(c), __ldg(c + 8), __ldg(c + 16), __ldg(c + 4), __ldg(c + 12), __ldg(c + 20), s.r)) pm &= ~(1u << k);
+            }
+            const unsigned int b0 = __ballot_sync(FULL, pm & 1u), b1 = __ballot_sync(FULL, pm & 2u);
+            const unsigned int b2 = __ballot_sync(FULL, pm & 4u), b3 = __ballot_sync(FULL, pm & 8u);
+            bool descended = false;
+            if (meta & WIDE_LEAF_BIT) {
+                // a reference leaf: every candidate primitive is tested by all its lanes together
+#pragma unroll 1
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned int bk = (k == 0 ? b0 : (k == 1 ? b1 : (k == 2 ? b2 : b3))) & alive;
+                    if (bk == 0u) continue;
+                    const int idx = first + k;
+                    const bool mine = (bk >> lane) & 1u;
+                    const unsigned int type = (meta >> (16 + 2 * k)) & 3u;  // warp-uniform
+                    Hit h;
+                    bool hit = false;
+                    if (type == RT_PLANE) { if (mine) hit = intersect_prim<false, PRIM_PLANE>(bvh.prims, idx, s.r, h); }
+                    else { if (mine) hit = intersect_prim<false, PRIM_XFORM>(bvh.prims, idx, s.r, h); }
+                    if (STATS && mine) st.prims++;
+                    if (hit) {
+                        if (ANY) { if (!(h.t > s.max_t)) { s.best_prim = 0; active = false; } }
+                        else if (h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) {
+                            s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
+                        }
+                    }
+                    if (ANY) alive = __ballot_sync(FULL, active);
+                }
+            } else if ((b0 | b1 | b2 | b3) != 0u) {
+                // inner node: children ordered by the packet's smallest entry parameter
+                int key[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned int bk = k == 0 ? b0 : (k == 1 ? b1 : (k == 2 ? b2 : b3));
+                    int v = 0x7fffffff;
+                    if (bk != 0u) {
+                        if (ANY) v = k;  // occlusion query: order does not matter
+                        else {
+                            const int mine = ((pm >> k) & 1u) ? __float_as_int(fmaxf(ent[k], 0.0f)) : 0x7fffffff;
+                            v = (__reduce_min_sync(FULL, mine) & ~3) | k;
+                        }
+                    }
+                    key[k] = v;
+                }
+#define RT_CSWAP(i, j) { const int lo_ = min(key[i], key[j]), hi_ = max(key[i], key[j]); key[i] = lo_; key[j] = hi_; }
+                RT_CSWAP(0, 1) RT_CSWAP(2, 3) RT_CSWAP(0, 2) RT_CSWAP(1, 3) RT_CSWAP(1, 2)
+#undef RT_CSWAP
+#pragma unroll
+                for (int j = 3; j >= 1; --j) {
+                    if (key[j] != 0x7fffffff) {
+                        const int slot = key[j] & 3;
+                        const unsigned int bk = slot == 0 ? b0 : (slot == 1 ? b1 : (slot == 2 ? b2 : b3));
+                        if (lane == 0)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %3};" :: "r"(sp), "r"(first + slot), "r"(bk), "r"(key[j]) : "memory");
+                        sp += 16u;
+                    }
+                }
+                const int slot = key[0] & 3;
+                cur = first + slot;
+                curmask = (slot == 0 ? b0 : (slot == 1 ? b1 : (slot == 2 ? b2 : b3))) & alive;
+                descended = curmask != 0u;
+            }
+            // ---- pop until an entry still has lanes that need it ----
+            __syncwarp();
+            while (!descended && sp != stk0) {
+                sp -= 16u;
+                int node, key, pad;
+                unsigned int mask;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(node), "=r"(mask), "=r"(key), "=r"(pad) : "r"(sp) : "memory");
+                mask &= alive;
+                if (!ANY) mask &= __ballot_sync(FULL, __int_as_float(key & ~3) <= s.lim);
+                if (mask != 0u) { cur = node; curmask = mask; descended = true; }
+            }
+            if (!descended) break;
+        }
+        if (traversing) src.store(item, s);
+    }
+}
+
 RT_DEV void flush_stats(const FrameParams& p, const TraceStats& st) {
     unsigned long long a = st.nodes, b = st.prims;
 #pragma unroll
@@ -263,11 +421,13 @@ RT_DEV void flush_stats(const FrameParams& p, const TraceStats& st) {
 struct ViewRays {
     const float4* __restrict__ q;
     int* hit_prim;
-    RT_DEV void load(long long item, Ray& r, float& max_t) const {
+    // false: a dead slot (padding of a level-0 packet)
+    RT_DEV bool load(long long item, Ray& r, float& max_t) const {
         const float4 a = q[(size_t)item * 3 + 0], b = q[(size_t)item * 3 + 1];
         r.ox = a.x; r.oy = a.y; r.oz = a.z; r.time = a.w;
         r.dx = b.x; r.dy = b.y; r.dz = b.z;
         max_t = 0.0f;
+        return !(b.x == 0.0f && b.y == 0.0f && b.z == 0.0f);
     }
     RT_DEV void store(long long item, const TravState& s) const { hit_prim[item] = s.best_prim; }
 };
@@ -324,12 +484,13 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
         }
         const uint32_t pixel = __float_as_uint(c.x), sample = __float_as_uint(c.y), node = __float_as_uint(c.z);
         const float weight = b.w;
-        if (live && prim < 0) {
+        const bool dead = pixel == RT_DEAD;  // padding slot of a level-0 packet
+        if (live && !dead && prim < 0) {
             const float bg = weight * 0.1f;  // background {0.1,0.1,0.1} (raytracer.cpp:297)
             accumulate(p, pixel, bg, bg, bg);
             if (node == 1u && sample == 0u && p.hit_ids) p.hit_ids[pixel] = -1;
         }
-        const bool hit = live && prim >= 0;
+        const bool hit = live && !dead && prim >= 0;
         Ray r;
         r.ox = a.x; r.oy = a.y; r.oz = a.z; r.time = a.w;
         r.dx = b.x; r.dy = b.y; r.dz = b.z;
@@ -348,8 +509,18 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
         }
         const float roughness = m2.z, reflectivity = m2.w, transparency = m3.x, ior = m3.y;
 
-        // shade record
-        const unsigned int rec = warp_reserve(lv + L_RECS, hit);
+        // shade record. Level 0 keeps record i for ray i (misses leave an invalid record) so that the
+        // shadow rays of a packet belong to one pixel block; deeper levels compact.
+        unsigned int rec;
+        if (level == 0) {
+            rec = i;
+            const unsigned int hits = __ballot_sync(0xffffffffu, hit);
+            if ((threadIdx.x & 31) == 0 && hits) atomicAdd(lv + L_LIVE_RECS, (unsigned int)__popc(hits));
+            if (i == 0) lv[L_RECS] = n;
+            if (live && !hit) p.recs[0][(size_t)rec * 5] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(RT_DEAD));
+        } else {
+            rec = warp_reserve(lv + L_RECS, hit);  // compact: the queue size is the live count
+        }
         if (hit) {
             const float4 m0 = __ldg(p.mats + 4 * mat + 0);
             float br, bg, bb;
@@ -427,6 +598,16 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
     }
 }
 
+template <bool STATS>
+__global__ void __launch_bounds__(RT_TRACE_THREADS, RT_TRACE_MINBLOCKS) trace_packet_kernel(const __grid_constant__ FrameParams p, int level) {
+    unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
+    const unsigned int n = min(lv[L_RAYS], (unsigned int)p.capacity);
+    TraceStats st = {0u, 0u};
+    ViewRays src = {p.q[level & 1], p.hit_prim};
+    packet_loop<false, STATS>(p.bvh, src, lv + L_WORK_TRACE, n, st);
+    if (STATS) flush_stats(p, st);
+}
+
 // ---------------------------------------------------------------------------------------------
 // shadow_kernel: one lane per shadow ray = (light, shade record, light sample), LIGHT-MAJOR: the
 // rays of a warp go to the same light from neighbouring surface points (or, for an area light,
@@ -439,7 +620,8 @@ struct ShadowRays {
     int* vis;
     unsigned int n_recs;
     int* vis_slot;
-    RT_DEV void load(long long item, Ray& sr, float& max_t) {
+    // false: the record is invalid (level 0: the view ray missed)
+    RT_DEV bool load(long long item, Ray& sr, float& max_t) {
         unsigned long long rest = (unsigned long long)item;
         int li = 0, cnt = 1;
         float4 l0, l1;
@@ -454,7 +636,9 @@ struct ShadowRays {
         }
         const unsigned int rec = (unsigned int)(rest / (unsigned int)cnt);
         const int k = (int)(rest % (unsigned int)cnt);
-        const float4 r0 = recs[(size_t)rec * 5 + 0], r1 = recs[(size_t)rec * 5 + 1];
+        const float4 r0 = recs[(size_t)rec * 5 + 0];
+        if (__float_as_uint(r0.w) == RT_DEAD) return false;
+        const float4 r1 = recs[(size_t)rec * 5 + 1];
         float tx = l0.x, ty = l0.y, tz = l0.z;
         const float radius = l1.w;
         if (radius > 0.0f) {
@@ -471,6 +655,7 @@ struct ShadowRays {
         sr.dx = lx; sr.dy = ly; sr.dz = lz;
         sr.time = 0.0f;  // `Ray shadowRay;` keeps the default time (shapes.hpp:28)
         vis_slot = vis + (size_t)rec * p.n_lights + li;
+        return true;
     }
     // nothing closer than the light: this sample is lit (raytracer.cpp:233-235)
     RT_DEV void store(long long, const TravState& s) const { if (s.best_prim < 0) atomicAdd(vis_slot, 1); }
@@ -486,6 +671,16 @@ __global__ void __launch_bounds__(RT_TRACE_THREADS, RT_TRACE_MINBLOCKS) shadow_k
     if (STATS) flush_stats(p, st);
 }
 
+template <bool STATS>
+__global__ void __launch_bounds__(RT_TRACE_THREADS, RT_TRACE_MINBLOCKS) shadow_packet_kernel(const __grid_constant__ FrameParams p, int level) {
+    unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
+    const unsigned long long n = (unsigned long long)lv[L_RECS] * (unsigned long long)p.shadow_per_rec;
+    TraceStats st = {0u, 0u};
+    ShadowRays src = {p, p.recs[level & 1], p.vis[level & 1], lv[L_RECS], nullptr};
+    packet_loop<true, STATS>(p.bvh, src, lv + L_WORK_SHADOW, n, st);
+    if (STATS) flush_stats(p, st);
+}
+
 // ---------------------------------------------------------------------------------------------
 // light_kernel: Blinn-Phong sum of one shade record with the visibilities from shadow_kernel.
 // shade() raytracer.cpp:191-273, then Trace()'s local_contribution * localColor.
@@ -494,7 +689,9 @@ __global__ void __launch_bounds__(256) light_kernel(const __grid_constant__ Fram
     const unsigned int n = p.lvl[level * RT_LVL_STRIDE + L_RECS];
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4* rc = p.recs[level & 1] + (size_t)i * 5;
-        const float4 r0 = rc[0], r1 = rc[1], r2 = rc[2], r3 = rc[3];
+        const float4 r0 = rc[0];
+        if (__float_as_uint(r0.w) == RT_DEAD) continue;  // level 0: ray i missed
+        const float4 r1 = rc[1], r2 = rc[2], r3 = rc[3];
         const int mat = __float_as_int(r2.w);
         const float4 m0 = __ldg(p.mats + 4 * mat + 0);
         const float4 m1 = __ldg(p.mats + 4 * mat + 1);
@@ -537,7 +734,9 @@ __global__ void fold_kernel(const __grid_constant__ FrameParams p) {
     const int level = threadIdx.x;
     if (level > RT_MAX_DEPTH + 1) return;
     unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
-    const unsigned long long rays = min(lv[L_RAYS], (unsigned int)p.capacity), recs = lv[L_RECS];
+    // level 0 queues have dead slots (packets = pixel blocks): its live counts are kept separately
+    const unsigned long long rays = level == 0 ? lv[L_LIVE_RAYS] : min(lv[L_RAYS], (unsigned int)p.capacity);
+    const unsigned long long recs = level == 0 ? lv[L_LIVE_RECS] : lv[L_RECS];
     if (rays) atomicAdd(p.totals + (level == 0 ? T_PRIMARY : T_SECONDARY), rays);
     if (recs) atomicAdd(p.totals + T_SHADOW, recs * (unsigned long long)p.shadow_per_rec);
     for (int k = 0; k < RT_LVL_STRIDE; ++k) lv[k] = 0u;
@@ -883,6 +1082,8 @@ static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time
     // pairs only depend on shade(d). The persistent kernels fill the GPU, so the overlap mostly
     // hides each kernel's tail behind the other's start. RT_B200_OVERLAP=0 serialises everything.
     static const bool overlap_enabled = [] { const char* e = std::getenv("RT_B200_OVERLAP"); return !(e && e[0] == '0'); }();
+    static const bool packet_enabled = [] { const char* e = std::getenv("RT_B200_PACKET"); return !(e && e[0] == '0'); }();
+    const size_t packet_smem = (size_t)(RT_TRACE_THREADS / 32) * d->stack_depth * 16;  // per-warp stacks only
     const bool overlap = overlap_enabled && !serial;
     if (overlap && !d->aux) CUDA_TRY(cudaStreamCreateWithFlags(&d->aux, cudaStreamNonBlocking));
     const cudaStream_t aux = overlap ? d->aux : stream;
@@ -903,9 +1104,16 @@ static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time
         gen_kernel<<<std::min(grid_wide, (n_units + 7) / 8), 256, 0, stream>>>(k, u0, n_units);
         ++launches;
         for (int level = 0; level <= k.max_depth; ++level) {
+            // level 0 is coherent (pixel blocks): packet traversal; deeper levels: per-ray traversal
+            const bool packets = packet_enabled && level == 0;
             int pr = mark_begin(0, stream);
-            if (collect) trace_kernel<true><<<grid_trace, RT_TRACE_THREADS, d->stack_bytes, stream>>>(k, level);
-            else trace_kernel<false><<<grid_trace, RT_TRACE_THREADS, d->stack_bytes, stream>>>(k, level);
+            if (packets) {
+                if (collect) trace_packet_kernel<true><<<grid_trace, RT_TRACE_THREADS, packet_smem, stream>>>(k, level);
+                else trace_packet_kernel<false><<<grid_trace, RT_TRACE_THREADS, packet_smem, stream>>>(k, level);
+            } else {
+                if (collect) trace_kernel<true><<<grid_trace, RT_TRACE_THREADS, d->stack_bytes, stream>>>(k, level);
+                else trace_kernel<false><<<grid_trace, RT_TRACE_THREADS, d->stack_bytes, stream>>>(k, level);
+            }
             mark_end(pr, stream);
             // shade(level) overwrites the record buffers that shadow/light of level - 2 read
             if (aux != stream && level >= 2) CUDA_TRY(cudaStreamWaitEvent(stream, d->ev_light[level - 2], 0));
@@ -918,8 +1126,13 @@ static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time
             }
             if (k.shadow_per_rec > 0) {
                 pr = mark_begin(1, aux);
-                if (collect) shadow_kernel<true><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, aux>>>(k, level);
-                else shadow_kernel<false><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, aux>>>(k, level);
+                if (packets) {
+                    if (collect) shadow_packet_kernel<true><<<grid_shadow, RT_TRACE_THREADS, packet_smem, aux>>>(k, level);
+                    else shadow_packet_kernel<false><<<grid_shadow, RT_TRACE_THREADS, packet_smem, aux>>>(k, level);
+                } else {
+                    if (collect) shadow_kernel<true><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, aux>>>(k, level);
+                    else shadow_kernel<false><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, aux>>>(k, level);
+                }
                 mark_end(pr, aux);
                 ++launches;
             }
