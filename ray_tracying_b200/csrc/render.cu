@@ -235,6 +235,7 @@ RT_DEV void wave_loop(const BvhView& bvh, Src& src, unsigned int* counter, unsig
     long long item = -1;
     unsigned int pool_lo = 0, pool_hi = 0;
     bool more = true;
+    const unsigned int pool = pool_size(n);
     while (true) {
         const unsigned int idle = __ballot_sync(FULL, item < 0);
         if (idle != 0u) {
@@ -242,7 +243,7 @@ RT_DEV void wave_loop(const BvhView& bvh, Src& src, unsigned int* counter, unsig
             if (!work) {
                 if (idle == FULL) break;
             } else if (idle == FULL || __popc(idle) >= RT_T_FETCH) {
-                const long long got = warp_take(counter, n, item < 0, pool_lo, pool_hi, more);
+                const long long got = warp_take(counter, n, item < 0, pool_lo, pool_hi, more, pool);
                 if (item < 0 && got >= 0) {
                     item = got;
                     Ray r;

@@ -681,19 +681,26 @@ RT_DEV void trav_prims(const BvhView& b, TravState& s, TraceStats& st) {
 // an item gets one. Returns the item index or -1. `more` turns false when the global counter has
 // passed n. All 32 lanes must call it together.
 #define RT_POOL 128u
+// Pool size for n items on this grid: 128 when there is plenty of work, down to 32 when there are
+// few items, so that a small wave spreads over many warps instead of queueing behind a few.
+RT_DEV unsigned int pool_size(unsigned long long n) {
+    const unsigned long long warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    const unsigned long long per_warp = (n + warps - 1) / warps;
+    return (unsigned int)min((unsigned long long)RT_POOL, max(32ull, (per_warp + 31ull) & ~31ull));
+}
 RT_DEV long long warp_take(unsigned int* counter, unsigned long long n, bool need, unsigned int& pool_lo, unsigned int& pool_hi,
-                           bool& more) {
+                           bool& more, unsigned int pool = RT_POOL) {
     const int lane = threadIdx.x & 31;
     long long item = -1;
     unsigned int mask = __ballot_sync(0xffffffffu, need);
     while (mask != 0u && (pool_lo < pool_hi || more)) {
         if (pool_lo >= pool_hi) {  // warp-uniform: get the next pool
             unsigned int base = 0;
-            if (lane == 0) base = atomicAdd(counter, RT_POOL);
+            if (lane == 0) base = atomicAdd(counter, pool);
             base = __shfl_sync(0xffffffffu, base, 0);
             if ((unsigned long long)base >= n) { more = false; break; }
             pool_lo = base;
-            pool_hi = (unsigned int)min((unsigned long long)base + RT_POOL, n);
+            pool_hi = (unsigned int)min((unsigned long long)base + pool, n);
         }
         const unsigned int avail = pool_hi - pool_lo;
         const unsigned int rank = (unsigned int)__popc(mask & ((1u << lane) - 1u));
