@@ -58,6 +58,9 @@ namespace rtb {
 #ifndef RT_TRACE_MINBLOCKS
 #define RT_TRACE_MINBLOCKS 6
 #endif
+#ifndef RT_ANY_SORTED_PACKET
+#define RT_ANY_SORTED_PACKET 0
+#endif
 #ifndef RT_STEPS_PER_VOTE
 #define RT_STEPS_PER_VOTE 3
 #endif
@@ -366,7 +369,7 @@ RT_DEV void packet_loop(const BvhView& bvh, Src& src, unsigned int* counter, uns
                     const unsigned int bk = k == 0 ? b0 : (k == 1 ? b1 : (k == 2 ? b2 : b3));
                     int v = 0x7fffffff;
                     if (bk != 0u) {
-                        if (ANY) v = k;  // occlusion query: order does not matter
+                        if (ANY && !RT_ANY_SORTED_PACKET) v = k;  // slot order
                         else {
                             const int mine = ((pm >> k) & 1u) ? __float_as_int(fmaxf(ent[k], 0.0f)) : 0x7fffffff;
                             v = (__reduce_min_sync(FULL, mine) & ~3) | k;

@@ -442,6 +442,11 @@ __device__ __noinline__ int4 traverse_exact_impl(const float4* __restrict__ prim
 // Closest-hit queries store (node, entry parameter) pairs -- RT_STACK_WORDS = 2, one 64-bit
 // access -- so that a popped sub-tree that starts beyond the current best hit is dropped without
 // visiting it; occlusion queries have a fixed limit and store the node only.
+// RT_ANY_SORTED: occlusion queries also visit children near-first (occluders tend to sit close to
+// the surface the shadow ray leaves) instead of in slot order.
+#ifndef RT_ANY_SORTED
+#define RT_ANY_SORTED 1
+#endif
 #ifndef RT_STACK_ENTRY_T
 #define RT_STACK_ENTRY_T 1
 #endif
@@ -581,7 +586,7 @@ RT_DEV void trav_step(const BvhView& b, TravState& s, unsigned int stride, Trace
         // a reference leaf's node: its passing children wait for the warp's next primitive phase
         s.pend = pm;
         s.pend_node = node;
-    } else if (ANY) {
+    } else if (ANY && !RT_ANY_SORTED) {
         // occlusion query: order does not matter
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -604,7 +609,7 @@ RT_DEV void trav_step(const BvhView& b, TravState& s, unsigned int stride, Trace
 #pragma unroll
         for (int j = 3; j >= 1; --j) {
             if (j < n) {
-                if (RT_STACK_ENTRY_T) stack_push2(sp, stride, first + (key[j] & 3), key[j]);
+                if (RT_STACK_ENTRY_T && !ANY) stack_push2(sp, stride, first + (key[j] & 3), key[j]);
                 else stack_push(sp, stride, first + (key[j] & 3));
             }
         }
