@@ -5,16 +5,19 @@
 // Replaces the reference frame loop raytracer.cpp:433-476 and everything it calls:
 //   compute_pixel_color + Camera::pixelToRay_thin_lens (raytracer.cpp:18-70, camera.cpp:97-178)
 //                                                     -> gen_kernel
-//   BVH::get_intersection for view rays (acceleration.cpp:142-150)   -> trace_kernel
+//   BVH::get_intersection for view rays (acceleration.cpp:142-150)   -> trace_packet_kernel (level 0:
+//                                                        one traversal per warp / pixel block),
+//                                                        trace_kernel (deeper levels: per-ray loop)
 //   Trace (raytracer.cpp:280-351): miss colour, reflection / refraction ray construction
 //                                                     -> shade_kernel (emits the next wave)
-//   shade (raytracer.cpp:180-274): shadow rays         -> shadow_kernel (one thread per shadow ray)
+//   shade (raytracer.cpp:180-274): shadow rays         -> shadow_packet_kernel / shadow_kernel
 //                                  Blinn-Phong sum     -> light_kernel
 //   gamma / clamp / quantise (raytracer.cpp:446-457)   -> finalize_kernel
 //
 // One batch = up to `batch_slots` (pixel, sample) pairs of this rank's screen tiles. For each
 // recursion level d = 0..max_depth the four kernels run over the level's ray queue; kernels read
-// their work size from device counters, so a whole frame is enqueued without host round trips.
+// their work size from device counters, so a whole frame is enqueued without host round trips;
+// shadow + light of level d run on a second stream and overlap trace + shade of level d+1.
 // The recursion tree of a sample is numbered (root 1, reflection 2k, refraction 2k+1); random
 // numbers are keyed by (pixel, sample, node, light, shadow sample), so the image does not depend
 // on queue order, batch size or tile sharding. Colour is accumulated per pixel in 64-bit fixed

@@ -5,7 +5,7 @@
 // division / square root, and every expression here is written in the reference's operand order,
 // so each float the reference computes on x86-64/SSE2 is reproduced bit for bit (transcendentals
 // excepted). Explicit __fmaf_rn is used ONLY in the conservative box test, which never decides a
-// result on its own (see box_maybe()).
+// result on its own (see wide_child_test()).
 //
 // Traversal semantics: the reference (acceleration.cpp:67-117) visits every node whose box the
 // ray passes, collects ALL leaf hits and returns the first minimum. Ancestor boxes contain leaf
