@@ -133,6 +133,29 @@ RT_DEV unsigned int warp_reserve(unsigned int* counter, bool want) {
     return base + (unsigned int)__popc(mask & ((1u << lane) - 1u));
 }
 
+// Block-level version for 256-thread blocks: consecutive slots for every thread with want == true,
+// ordered by thread index, with ONE atomic per block -- so that the queue keeps runs of up to 256
+// rays from one 32x8 pixel region together (coherent pools for the next level's traversal).
+// Optionally reserves a second class right behind the first (want2). `sh` = 20 words of shared
+// memory. MUST be called by all threads of the block.
+RT_DEV void block_reserve2(unsigned int* counter, bool want1, bool want2, unsigned int* sh, unsigned int& slot1, unsigned int& slot2) {
+    const unsigned int m1 = __ballot_sync(0xffffffffu, want1), m2 = __ballot_sync(0xffffffffu, want2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sh[warp] = (unsigned int)__popc(m1); sh[8 + warp] = (unsigned int)__popc(m2); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int run = 0;
+        for (int w = 0; w < 16; ++w) { const unsigned int c = sh[w]; sh[w] = run; run += c; }  // exclusive prefix, class 1 then 2
+        sh[16] = run ? atomicAdd(counter, run) : 0u;
+    }
+    __syncthreads();
+    const unsigned int base = sh[16];
+    const unsigned int lt = (1u << lane) - 1u;
+    slot1 = base + sh[warp] + (unsigned int)__popc(m1 & lt);
+    slot2 = base + sh[8 + warp] + (unsigned int)__popc(m2 & lt);
+    __syncthreads();  // sh is reused by the next call
+}
+
 // ---------------------------------------------------------------------------------------------
 // gen_kernel: primary rays of units [unit0, unit0 + n_units); a unit = (8x4 pixel block, sample),
 // one lane per pixel. compute_pixel_color + Camera::pixelToRay_thin_lens.
@@ -480,7 +503,8 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
     const unsigned int n = min(lv[L_RAYS], (unsigned int)p.capacity);
     const float4* __restrict__ q = p.q[level & 1];
     float4* __restrict__ qn = p.q[(level + 1) & 1];
-    const unsigned int n_round = (n + 31u) & ~31u;  // whole warps take part in warp_reserve
+    __shared__ unsigned int sh_reserve[20];
+    const unsigned int n_round = (n + 255u) & ~255u;  // whole 256-thread blocks take part in block_reserve2
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         const bool live = i < n;
         int prim = -1;
@@ -526,7 +550,8 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
             if (i == 0) lv[L_RECS] = n;
             if (live && !hit) p.recs[0][(size_t)rec * 5] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(RT_DEAD));
         } else {
-            rec = warp_reserve(lv + L_RECS, hit);  // compact: the queue size is the live count
+            unsigned int unused;
+            block_reserve2(lv + L_RECS, hit, false, sh_reserve, rec, unused);  // compact: the queue size is the live count
         }
         if (hit) {
             const float4 m0 = __ldg(p.mats + 4 * mat + 0);
@@ -580,8 +605,8 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
                 want_refr = dot3(tx, ty, tz, tx, ty, tz) > 1e-6f;
             }
         }
-        const unsigned int s_refl = warp_reserve(lv_next + L_RAYS, want_refl);
-        const unsigned int s_refr = warp_reserve(lv_next + L_RAYS, want_refr);
+        unsigned int s_refl, s_refr;  // the block's reflection rays, then its refraction rays
+        block_reserve2(lv_next + L_RAYS, want_refl, want_refr, sh_reserve, s_refl, s_refr);
         if (want_refl) {
             if (s_refl < (unsigned int)p.capacity) {
                 float4* o = qn + (size_t)s_refl * 3;  // secondary rays carry the default time 0 (shapes.hpp:28)
