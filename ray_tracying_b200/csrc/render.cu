@@ -1137,7 +1137,8 @@ static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time
         ++launches;
         for (int level = 0; level <= k.max_depth; ++level) {
             // level 0 is coherent (pixel blocks): packet traversal; deeper levels: per-ray traversal
-            const bool packets = packet_enabled && level == 0;
+            static const int packet_levels = [] { const char* e = std::getenv("RT_B200_PACKET_LEVELS"); return e ? std::atoi(e) : 0; }();
+            const bool packets = packet_enabled && level <= packet_levels;
             int pr = mark_begin(0, stream);
             if (packets) {
                 if (collect) trace_packet_kernel<true><<<grid_trace, RT_TRACE_THREADS, packet_smem, stream>>>(k, level);
