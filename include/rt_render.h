@@ -199,7 +199,11 @@ int rt_shard_pixels(const rt_scene* scene, const rt_render_params* p, int64_t* n
  *   hit_ids : width*height int32, load-order index of the primitive hit by the first sample's
  *             primary ray, -1 = background; may be NULL
  *   linear  : width*height*3 float, averaged linear colour before gamma; may be NULL
- * Full-frame buffers; a rank with world > 1 writes only the pixels of its own tiles. */
+ * Full-frame buffers; a rank with world > 1 writes only the pixels of its own tiles.
+ * Ray queues have a fixed capacity; a scene whose ray trees branch heavily (reflective AND
+ * transparent materials) can overflow them, which a synchronous call (stats != NULL) detects and
+ * answers by re-rendering with smaller batches, remembered for later calls on this scene. Call once
+ * synchronously before a series of asynchronous calls (bench.py's counting pass does). */
 int rt_render_device(rt_scene* scene, const rt_render_params* p, uint8_t* rgb8, int32_t* hit_ids, float* linear,
                      void* stream, rt_render_stats* stats);
 

@@ -261,6 +261,7 @@ RT_DEV void wave_loop(const BvhView& bvh, Src& src, unsigned int* counter, unsig
     s.pend = 0u;
     s.sp0 = (unsigned int)__cvta_generic_to_shared(rt_stack_smem + threadIdx.x * words);
     s.sp = s.sp0;
+    s.sp_end = s.sp0 + (unsigned int)bvh.stack_depth * stride;
     long long item = -1;
     unsigned int pool_lo = 0, pool_hi = 0;
     bool more = true;
@@ -414,6 +415,7 @@ RT_DEV void packet_loop(const BvhView& bvh, Src& src, unsigned int* counter, uns
                         if (lane == 0)
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %3};" :: "r"(sp), "r"(first + slot), "r"(bk), "r"(key[j]) : "memory");
                         sp += 16u;
+                        if (RT_CHECKS && sp > stk0 + (unsigned int)bvh.stack_depth * 16u) __trap();
                     }
                 }
                 const int slot = key[0] & 3;
@@ -1073,7 +1075,9 @@ static int ensure_buffers(DeviceScene* d, const FrameParams& k, long long batch_
 static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time_classes, bool serial, uint8_t* rgb8, float* linear,
                          cudaStream_t stream) {
     const long long total_units = (long long)k.n_my_tiles * k.sub_per_tile * k.spp;  // unit = 32 (pixel, sample) slots
-    const long long batch_units = std::max<long long>(1, std::min<long long>(std::max<long long>(total_units, 1), d->batch_slots / 32));
+    // work counters are 32-bit: keep (slots of a batch) x (shadow rays per shaded hit) below 2^31
+    const long long slot_cap = std::max<long long>(32, (1ll << 31) / std::max(1, k.shadow_per_rec));
+    const long long batch_units = std::max<long long>(1, std::min<long long>(std::max<long long>(total_units, 1), std::min(d->batch_slots, slot_cap) / 32));
     int rc = ensure_buffers(d, k, batch_units * 32);
     if (rc != RT_OK) return rc;
     k.q[0] = d->q[0]; k.q[1] = d->q[1];

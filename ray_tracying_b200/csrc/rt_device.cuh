@@ -451,6 +451,11 @@ __device__ __noinline__ int4 traverse_exact_impl(const float4* __restrict__ prim
 #define RT_STACK_ENTRY_T 1
 #endif
 #define RT_STACK_WORDS (RT_STACK_ENTRY_T ? 2 : 1)
+// RT_CHECKS=1 (debug builds, scripts: make variant NAME=checks NVCC_EXTRA=-DRT_CHECKS=1): trap on a
+// traversal-stack overflow instead of corrupting a neighbour's stack.
+#ifndef RT_CHECKS
+#define RT_CHECKS 0
+#endif
 RT_DEV void stack_push(unsigned int& sp, unsigned int stride_bytes, int v) {
     asm volatile("st.shared.b32 [%0], %1;" :: "r"(sp), "r"(v) : "memory");
     sp += stride_bytes;
@@ -485,6 +490,7 @@ struct TravState {
     int cur;           // wide node to visit next, RT_CUR_NONE when there is none
     unsigned int sp;   // shared-space address of the next free stack entry
     unsigned int sp0;  // ... of entry 0 (stack empty when sp == sp0)
+    unsigned int sp_end;  // RT_CHECKS: address one past the last entry
     unsigned int pend; // bit k: child k of node pend_node is a primitive waiting for its test
     int pend_node;
 };
@@ -615,6 +621,7 @@ RT_DEV void trav_step(const BvhView& b, TravState& s, unsigned int stride, Trace
         }
         if (n > 0) next = first + (key[0] & 3);
     }
+    if (RT_CHECKS && sp > s.sp_end) __trap();
     if (!ANY && RT_STACK_ENTRY_T) {
         // drop popped sub-trees that start beyond the best hit (the key's low 2 bits are the slot:
         // clearing them only lowers the entry bound for positive entries; negative ones always pass)
