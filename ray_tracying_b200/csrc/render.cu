@@ -848,7 +848,9 @@ struct DeviceScene {
     size_t accum_pixels = 0;
     unsigned int* lvl = nullptr;
     unsigned long long* totals = nullptr;
-    long long batch_slots = 3ll << 20;  // (pixel, sample) pairs per batch; halved on queue overflow
+    // (pixel, sample) pairs per batch; halved on queue overflow. Large batches keep the waves of the
+    // deeper recursion levels big (a level of a batch is one launch); RT_B200_BATCH_SLOTS overrides.
+    long long batch_slots = [] { const char* e = std::getenv("RT_B200_BATCH_SLOTS"); return e ? std::atoll(e) : (8ll << 20); }();
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     int sm_count = 0;
     int trace_blocks = 1, shadow_blocks = 1;  // resident blocks per SM
@@ -1120,6 +1122,8 @@ static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time
     static const bool overlap_enabled = [] { const char* e = std::getenv("RT_B200_OVERLAP"); return !(e && e[0] == '0'); }();
     static const bool packet_enabled = [] { const char* e = std::getenv("RT_B200_PACKET"); return !(e && e[0] == '0'); }();
     const size_t packet_smem = (size_t)(RT_TRACE_THREADS / 32) * d->stack_depth * 16;  // per-warp stacks only
+    static const bool area_packets_enabled = [] { const char* e = std::getenv("RT_B200_AREA_PACKETS"); return !(e && e[0] == '0'); }();
+    const bool area_light_packets = area_packets_enabled && k.light_samples >= 8 && k.shadow_per_rec >= k.light_samples;
     const bool overlap = overlap_enabled && !serial;
     if (overlap && !d->aux) CUDA_TRY(cudaStreamCreateWithFlags(&d->aux, cudaStreamNonBlocking));
     const cudaStream_t aux = overlap ? d->aux : stream;
@@ -1143,6 +1147,8 @@ static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time
             // level 0 is coherent (pixel blocks): packet traversal; deeper levels: per-ray traversal
             static const int packet_levels = [] { const char* e = std::getenv("RT_B200_PACKET_LEVELS"); return e ? std::atoi(e) : 0; }();
             const bool packets = packet_enabled && level <= packet_levels;
+            // the samples of an area light leave one point: coherent at every level
+            const bool shadow_packets = packets || (packet_enabled && area_light_packets);
             int pr = mark_begin(0, stream);
             if (packets) {
                 if (collect) trace_packet_kernel<true><<<grid_trace, RT_TRACE_THREADS, packet_smem, stream>>>(k, level);
@@ -1163,7 +1169,7 @@ static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time
             }
             if (k.shadow_per_rec > 0) {
                 pr = mark_begin(1, aux);
-                if (packets) {
+                if (shadow_packets) {
                     if (collect) shadow_packet_kernel<true><<<grid_shadow, RT_TRACE_THREADS, packet_smem, aux>>>(k, level);
                     else shadow_packet_kernel<false><<<grid_shadow, RT_TRACE_THREADS, packet_smem, aux>>>(k, level);
                 } else {
