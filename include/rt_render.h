@@ -168,6 +168,12 @@ typedef struct rt_bvh_node_dump {
 } rt_bvh_node_dump;
 int rt_scene_dump_bvh(const rt_scene* scene, rt_bvh_node_dump* out, int32_t max_nodes);
 
+/* The flattened 4-wide device tree (host copy), 32 floats per node, layout in
+ * ray_tracying_b200/csrc/scene.hpp (DWide): child boxes as structure of arrays, first child, meta
+ * word (valid / gate masks, leaf flag, primitive types), sphere cull coefficient. Writes at most
+ * max_nodes nodes, returns the number of nodes of the tree; *depth = its number of levels. */
+int rt_scene_dump_wide(const rt_scene* scene, float* out, int32_t max_nodes, int32_t* depth);
+
 /* Copies primitives, nodes, materials, lights and textures to the current CUDA device (the
  * "scene resident in HBM" state). Idempotent; rt_render* call it on demand. `bytes` (optional)
  * receives the number of bytes copied host->device. */

@@ -104,6 +104,7 @@ SYMBOLS = {
     "rt_scene_last_timing": (C.c_int, [_VP, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "rt_shard_pixels": (C.c_int, [_VP, C.POINTER(RenderParams), C.POINTER(C.c_int64)]),
     "rt_render_device": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _VP, _VP, _VP, C.POINTER(RenderStats)]),
+    "rt_scene_dump_wide": (C.c_int, [_VP, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32)]),
     "rt_scene_last_kernel_times": (C.c_int, [_VP, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "rt_render": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _VP, _VP, C.POINTER(RenderStats)]),
     "rt_write_ppm": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, _VP]),

@@ -163,6 +163,16 @@ class Scene:
             check(got, "rt_scene_dump_bvh")
         return [(b.is_leaf, tuple(b.box_min), tuple(b.box_max), [b.prims[k] for k in range(b.count)]) for b in buf[:got]]
 
+    def dump_wide(self):
+        """(nodes, depth): the 4-wide device tree as an (N, 32) float32 array (csrc/scene.hpp DWide) and its depth."""
+        depth = C.c_int32()
+        n = lib.rt_scene_dump_wide(self._h, None, 0, C.byref(depth))
+        if n < 0:
+            check(n, "rt_scene_dump_wide")
+        out = np.zeros((max(n, 1), 32), dtype=np.float32)
+        check(min(0, lib.rt_scene_dump_wide(self._h, out.ctypes.data_as(C.POINTER(C.c_float)), n, C.byref(depth))), "rt_scene_dump_wide")
+        return out[:n], depth.value
+
     # -- device -------------------------------------------------------------------------------
     def upload(self) -> int:
         n = C.c_uint64()

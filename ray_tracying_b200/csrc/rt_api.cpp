@@ -128,6 +128,15 @@ int rt_scene_dump_bvh(const rt_scene* scene, rt_bvh_node_dump* out, int32_t max_
     return n;
 }
 
+int rt_scene_dump_wide(const rt_scene* scene, float* out, int32_t max_nodes, int32_t* depth) {
+    if (!scene || (!out && max_nodes > 0)) { rtb::set_error("null argument"); return RT_ERR_INVALID; }
+    const HostScene& h = scene->host;
+    const int32_t n = (int32_t)std::min<size_t>(h.dwide.size(), (size_t)std::max(0, max_nodes));
+    if (n > 0) std::memcpy(out, h.dwide.data(), (size_t)n * sizeof(rtb::DWide));
+    if (depth) *depth = h.wide_depth;
+    return (int32_t)h.dwide.size();
+}
+
 int rt_write_ppm(const char* path, int32_t width, int32_t height, const uint8_t* rgb8) {
     if (!path || !rgb8 || width <= 0 || height <= 0) { rtb::set_error("rt_write_ppm: bad argument"); return RT_ERR_INVALID; }
     if (!rtb::write_ppm_p3(path, width, height, rgb8)) { rtb::set_error(std::string("rt_write_ppm: cannot write ") + path); return RT_ERR_IO; }
