@@ -361,6 +361,16 @@ def run_ours(args, wl):
         if os.path.exists(tp):
             with open(tp) as f:
                 traffic = json.load(f).get(args.workload)
+        # what actually bounds the loop (committed ncu capture of this workload, not measured in this run):
+        # issue-slot utilisation and active lanes per instruction of the traversal kernels
+        ncu_note = None
+        kp = os.path.join(ROOT, "profiles", "ncu_key_metrics.json")
+        if os.path.exists(kp) and args.workload == "mixed100k":
+            with open(kp) as f:
+                km = json.load(f)
+            ncu_note = {"source": km["source"],
+                        "kernels": {k.replace("void ", ""): {m: round(v[0][m], 2) for m in ("issue_slot_pct", "lanes_per_instruction", "l1_hit_pct", "warps_active_pct")}
+                                    for k, v in km["kernels"].items()}}
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -383,7 +393,8 @@ def run_ours(args, wl):
                          "algorithmic_bytes_per_launch": alg_bytes // world // n_launch,
                          "share_of_step": trav / float(np.mean(serial_ms)), "serialised_step_ms": float(np.mean(serial_ms)),
                          "timing": "CUDA events around each launch, launches serialised on one stream (roofline leg)",
-                         "note": "scene is L2/L1 resident: DRAM traffic is ~1% of the algorithmic bytes, the loop is issue-bound",
+                         "note": "scene is L2/L1 resident: DRAM traffic is a few % of the algorithmic bytes, the loop is issue-bound",
+                         "ncu": ncu_note,
                          "box_tests_per_ray": node_visits / max(rays, 1), "prim_tests_per_ray": prim_tests / max(rays, 1)},
             "clocks": clock_info,
             "host": {"scene_load_and_bvh_build_s": load_s},
