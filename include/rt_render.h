@@ -218,6 +218,18 @@ int rt_render_device(rt_scene* scene, const rt_render_params* p, uint8_t* rgb8, 
 int rt_render(rt_scene* scene, const rt_render_params* p, uint8_t* rgb8, int32_t* hit_ids, float* linear,
               rt_render_stats* stats);
 
+/* Self-tests of the exactness machinery on the device (tests/test_gpu_properties.py).
+ * rt_selftest_boxes: n random (ray, box) pairs -- generic, near-axis-parallel directions, huge
+ *   coordinates, grazing faces / edges / corners to a few ulps -- through the conservative slab test
+ *   and the reference's exact AABB::intersect (shapes.cpp:55-72). out8 = {tests, exact passes,
+ *   conservative passes, surely passes, VIOLATIONS exact && !conservative, VIOLATIONS surely &&
+ *   !exact, rays skipped because a direction component is <= 1e-6, 0}.
+ * rt_selftest_cull: for every primitive of the scene, rays_per_primitive rays aimed at and around it
+ *   from near and far: the exact intersection routine against the conservative test of the
+ *   primitive's culling box. out8 = {tests, exact hits, culling passes, VIOLATIONS hit && !pass, ...}. */
+int rt_selftest_boxes(uint64_t seed, int64_t n, uint64_t* out8);
+int rt_selftest_cull(rt_scene* scene, uint64_t seed, int32_t rays_per_primitive, uint64_t* out8);
+
 /* Replaces Image::write / Image::read (image.cpp:53-84, 86-133): ASCII P3 PPM. */
 int rt_write_ppm(const char* path, int32_t width, int32_t height, const uint8_t* rgb8);
 int rt_read_ppm(const char* path, int32_t* width, int32_t* height, uint8_t** rgb8 /* free with rt_free */);

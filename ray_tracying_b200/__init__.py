@@ -5,10 +5,10 @@ shading with shadow, reflection and refraction rays, behind a C ABI (include/rt_
 Importing this package loads ``librt_b200.so``; it raises if the library has not been built.
 """
 from .api import (MAX_RECURSION_DEPTH, MATERIAL_DTYPE, SHAPE_DTYPE, Scene, Stats, device_count, make_params, read_ppm,
-                  write_ppm)
+                  selftest_boxes, write_ppm)
 from ._lib import RT_CUBE, RT_PLANE, RT_RECTANGLE, RT_SPHERE, RtError
 
 __all__ = [
     "MAX_RECURSION_DEPTH", "MATERIAL_DTYPE", "SHAPE_DTYPE", "Scene", "Stats", "device_count", "make_params",
-    "read_ppm", "write_ppm", "RT_SPHERE", "RT_CUBE", "RT_RECTANGLE", "RT_PLANE", "RtError",
+    "read_ppm", "write_ppm", "selftest_boxes", "RT_SPHERE", "RT_CUBE", "RT_RECTANGLE", "RT_PLANE", "RtError",
 ]

@@ -163,6 +163,12 @@ class Scene:
             check(got, "rt_scene_dump_bvh")
         return [(b.is_leaf, tuple(b.box_min), tuple(b.box_max), [b.prims[k] for k in range(b.count)]) for b in buf[:got]]
 
+    def selftest_cull(self, rays_per_primitive: int = 64, seed: int = 1) -> dict:
+        """rt_selftest_cull: exact primitive hits vs the conservative test of the culling boxes."""
+        out = (C.c_uint64 * 8)()
+        check(lib.rt_selftest_cull(self._h, seed, rays_per_primitive, out), "rt_selftest_cull")
+        return dict(zip(("tests", "hits", "passes", "violations"), (int(v) for v in out)))
+
     def dump_wide(self):
         """(nodes, depth): the 4-wide device tree as an (N, 32) float32 array (csrc/scene.hpp DWide) and its depth."""
         depth = C.c_int32()
@@ -253,6 +259,14 @@ def read_ppm(path: str) -> np.ndarray:
         return np.ctypeslib.as_array(ptr, shape=(h.value, w.value, 3)).copy()
     finally:
         lib.rt_free(ptr)
+
+
+def selftest_boxes(n: int, seed: int = 1) -> dict:
+    """rt_selftest_boxes: conservative slab test vs the reference's exact box test on n random pairs."""
+    out = (C.c_uint64 * 8)()
+    check(lib.rt_selftest_boxes(seed, n, out), "rt_selftest_boxes")
+    keys = ("tests", "exact", "conservative", "surely", "violations_exact_not_conservative", "violations_surely_not_exact", "skipped")
+    return dict(zip(keys, (int(v) for v in out)))
 
 
 def device_count() -> int:

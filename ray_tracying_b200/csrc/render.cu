@@ -763,6 +763,130 @@ __global__ void __launch_bounds__(256) light_kernel(const __grid_constant__ Fram
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Self-tests of the exactness machinery (called by tests/test_gpu_properties.py through the C ABI).
+// ---------------------------------------------------------------------------------------------
+RT_DEV float st_uniform(uint32_t a, uint32_t b, uint32_t c, uint32_t lane_word) {
+    const U4 u = philox4x32_10(U4{a, b, c, 0x51u}, 0xA5A5A5A5u, 0x0F0F0F0Fu);
+    const uint32_t w = lane_word == 0 ? u.x : (lane_word == 1 ? u.y : (lane_word == 2 ? u.z : u.w));
+    return u32_to_unit_float(w);
+}
+
+// out[0] tests, out[1] exact passes, out[2] conservative passes, out[3] surely,
+// out[4] VIOLATION exact && !conservative, out[5] VIOLATION surely && !exact, out[6] rays skipped (|d_i| <= 1e-6)
+__global__ void selftest_box_kernel(uint32_t seed, long long n, unsigned long long* out) {
+    unsigned long long c_exact = 0, c_pass = 0, c_sure = 0, v1 = 0, v2 = 0, skipped = 0, tests = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t lo32 = (uint32_t)i, hi32 = (uint32_t)(i >> 32) ^ seed;
+        auto rnd = [&](uint32_t k) { return st_uniform(lo32, hi32, k >> 2, k & 3u); };
+        const int mode = (int)(rnd(0) * 6.0f);  // 0,1 generic; 2 tiny direction component; 3 huge coordinates; 4,5 grazing
+        Ray r;
+        const float span = mode == 3 ? 2.0e4f : 100.0f;
+        r.ox = (rnd(1) * 2.0f - 1.0f) * span; r.oy = (rnd(2) * 2.0f - 1.0f) * span; r.oz = (rnd(3) * 2.0f - 1.0f) * span;
+        r.dx = rnd(4) * 2.0f - 1.0f; r.dy = rnd(5) * 2.0f - 1.0f; r.dz = rnd(6) * 2.0f - 1.0f;
+        if (mode == 2) {  // one component between 1e-6 and 1e-2 (log-uniform)
+            const float tiny = exp2f(-20.0f + 13.0f * rnd(7)) * (rnd(8) < 0.5f ? -1.0f : 1.0f);
+            const int ax = (int)(rnd(9) * 3.0f);
+            if (ax == 0) r.dx = tiny; else if (ax == 1) r.dy = tiny; else r.dz = tiny;
+        }
+        normalize3(r.dx, r.dy, r.dz);
+        r.time = 0.0f;
+        // box: log-uniform size, centre near a point on the ray (or behind it, or around the origin)
+        const float t0 = (rnd(10) * 1.3f - 0.3f) * 150.0f;
+        const float sx = exp2f(-10.0f + 16.0f * rnd(11)), sy = exp2f(-10.0f + 16.0f * rnd(12)), sz = exp2f(-10.0f + 16.0f * rnd(13));
+        float cx = r.ox + t0 * r.dx, cy = r.oy + t0 * r.dy, cz = r.oz + t0 * r.dz;
+        float offx, offy, offz;
+        if (mode >= 4) {
+            // grazing: the point of the ray sits on a face / edge / corner of the box, up to a few ulps
+            const float e = (rnd(14) * 2.0f - 1.0f) * 4e-7f;
+            offx = (rnd(15) < 0.5f ? -1.0f : 1.0f) * (1.0f + e);
+            offy = rnd(16) < 0.6f ? (rnd(17) < 0.5f ? -1.0f : 1.0f) * (1.0f + e) : (rnd(17) * 2.0f - 1.0f);
+            offz = rnd(18) < 0.3f ? (rnd(19) < 0.5f ? -1.0f : 1.0f) * (1.0f - e) : (rnd(19) * 2.0f - 1.0f);
+        } else {
+            offx = (rnd(15) * 2.0f - 1.0f) * 1.5f; offy = (rnd(16) * 2.0f - 1.0f) * 1.5f; offz = (rnd(17) * 2.0f - 1.0f) * 1.5f;
+        }
+        cx += offx * sx; cy += offy * sy; cz += offz * sz;
+        const float lox = cx - sx, hix = cx + sx, loy = cy - sy, hiy = cy + sy, loz = cz - sz, hiz = cz + sz;
+        if (fabsf(r.dx) <= 1e-6f || fabsf(r.dy) <= 1e-6f || fabsf(r.dz) <= 1e-6f) { skipped++; continue; }
+        TravState s;
+        s.r = r;
+        s.ix = 1.0f / r.dx; s.iy = 1.0f / r.dy; s.iz = 1.0f / r.dz;
+        {   // the same set-up as trav_begin
+            const float nx = -(r.ox * s.ix), ny = -(r.oy * s.iy), nz = -(r.oz * s.iz);
+            const float ex = 1.2e-7f * fabsf(nx) + 1e-35f, ey = 1.2e-7f * fabsf(ny) + 1e-35f, ez = 1.2e-7f * fabsf(nz) + 1e-35f;
+            s.nxl = s.ix > 0.0f ? nx - ex : nx + ex; s.nxh = s.ix > 0.0f ? nx + ex : nx - ex;
+            s.nyl = s.iy > 0.0f ? ny - ey : ny + ey; s.nyh = s.iy > 0.0f ? ny + ey : ny - ey;
+            s.nzl = s.iz > 0.0f ? nz - ez : nz + ez; s.nzh = s.iz > 0.0f ? nz + ez : nz - ez;
+            s.KS = 4.0f * fmaxf(fmaxf(ex, ey), ez);
+            s.imax = fmaxf(fmaxf(fabsf(s.ix), fabsf(s.iy)), fabsf(s.iz));
+        }
+        s.lim = FLT_MAX;
+        bool pass, sure;
+        float ent, tn;
+        wide_child_test(s, lox, hix, loy, hiy, loz, hiz, 0.0f, pass, sure, ent);
+        const bool exact = box_exact(lox, loy, loz, hix, hiy, hiz, r, tn);
+        tests++;
+        c_exact += exact; c_pass += pass; c_sure += sure;
+        v1 += exact && !pass;
+        v2 += sure && !exact;
+    }
+    atomicAdd(out + 0, tests); atomicAdd(out + 1, c_exact); atomicAdd(out + 2, c_pass); atomicAdd(out + 3, c_sure);
+    atomicAdd(out + 4, v1); atomicAdd(out + 5, v2); atomicAdd(out + 6, skipped);
+}
+
+// For every primitive child of every leaf node of the wide tree and `per_prim` rays aimed at / around
+// it: if the exact intersection routine reports a hit, the conservative test of its culling box must
+// pass. out[0] tests, out[1] exact hits, out[2] culling passes, out[3] VIOLATION hit && !pass.
+__global__ void selftest_cull_kernel(BvhView b, int n_nodes, int per_prim, uint32_t seed, float scene_span, unsigned long long* out) {
+    unsigned long long tests = 0, hits = 0, passes = 0, viol = 0;
+    const long long total = (long long)n_nodes * 4 * per_prim;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int node = (int)(i / (4 * per_prim)), k = (int)((i / per_prim) & 3);
+        const float* w = b.wide + (size_t)node * 32;
+        const unsigned int meta = __float_as_uint(__ldg(w + 25));
+        if (!(meta & WIDE_LEAF_BIT) || !((meta >> k) & 1u)) continue;
+        const int idx = __float_as_int(__ldg(w + 24)) + k;
+        const float lox = __ldg(w + k), hix = __ldg(w + 4 + k), loy = __ldg(w + 8 + k), hiy = __ldg(w + 12 + k), loz = __ldg(w + 16 + k), hiz = __ldg(w + 20 + k);
+        if (!(hix - lox < 1e29f)) continue;  // unbounded culling box: never skipped
+        const uint32_t lo32 = (uint32_t)i, hi32 = (uint32_t)(i >> 32) ^ seed;
+        auto rnd = [&](uint32_t q) { return st_uniform(lo32, hi32, 16u + (q >> 2), q & 3u); };
+        // origin: near, mid or far (up to the scene span) from the box; target: a point in the box
+        // stretched by 1.2 (so that many rays graze or just miss)
+        const float cx = 0.5f * (lox + hix), cy = 0.5f * (loy + hiy), cz = 0.5f * (loz + hiz);
+        const float ex = 0.5f * (hix - lox), ey = 0.5f * (hiy - loy), ez = 0.5f * (hiz - loz);
+        const float dist = exp2f(-3.0f + rnd(0) * (log2f(scene_span) + 3.0f));
+        float ux = rnd(1) * 2.0f - 1.0f, uy = rnd(2) * 2.0f - 1.0f, uz = rnd(3) * 2.0f - 1.0f;
+        normalize3(ux, uy, uz);
+        Ray r;
+        r.ox = cx + ux * dist; r.oy = cy + uy * dist; r.oz = cz + uz * dist;
+        const float tx = cx + (rnd(4) * 2.0f - 1.0f) * 1.2f * ex, ty = cy + (rnd(5) * 2.0f - 1.0f) * 1.2f * ey, tz = cz + (rnd(6) * 2.0f - 1.0f) * 1.2f * ez;
+        r.dx = tx - r.ox; r.dy = ty - r.oy; r.dz = tz - r.oz;
+        normalize3(r.dx, r.dy, r.dz);
+        r.time = rnd(7);
+        if (fabsf(r.dx) <= 1e-6f || fabsf(r.dy) <= 1e-6f || fabsf(r.dz) <= 1e-6f) continue;
+        Hit h;
+        const bool hit = intersect_prim<false>(b.prims, idx, r, h);
+        TravState s;
+        s.r = r;
+        s.ix = 1.0f / r.dx; s.iy = 1.0f / r.dy; s.iz = 1.0f / r.dz;
+        {
+            const float nx = -(r.ox * s.ix), ny = -(r.oy * s.iy), nz = -(r.oz * s.iz);
+            const float e0 = 1.2e-7f * fabsf(nx) + 1e-35f, e1 = 1.2e-7f * fabsf(ny) + 1e-35f, e2 = 1.2e-7f * fabsf(nz) + 1e-35f;
+            s.nxl = s.ix > 0.0f ? nx - e0 : nx + e0; s.nxh = s.ix > 0.0f ? nx + e0 : nx - e0;
+            s.nyl = s.iy > 0.0f ? ny - e1 : ny + e1; s.nyh = s.iy > 0.0f ? ny + e1 : ny - e1;
+            s.nzl = s.iz > 0.0f ? nz - e2 : nz + e2; s.nzh = s.iz > 0.0f ? nz + e2 : nz - e2;
+            s.KS = 4.0f * fmaxf(fmaxf(e0, e1), e2);
+            s.imax = fmaxf(fmaxf(fabsf(s.ix), fabsf(s.iy)), fabsf(s.iz));
+        }
+        s.lim = FLT_MAX;
+        bool pass, sure;
+        float ent;
+        wide_child_test(s, lox, hix, loy, hiy, loz, hiz, __ldg(w + 26) * s.imax, pass, sure, ent);
+        tests++; hits += hit; passes += pass; viol += hit && !pass;
+    }
+    atomicAdd(out + 0, tests); atomicAdd(out + 1, hits); atomicAdd(out + 2, passes); atomicAdd(out + 3, viol);
+}
+
 // Folds the per-level counters of a finished batch into the frame totals and clears them.
 __global__ void fold_kernel(const __grid_constant__ FrameParams p) {
     const int level = threadIdx.x;
@@ -1355,6 +1479,40 @@ int rt_scene_last_kernel_times(rt_scene* scene, float* ms4, int32_t* launches4, 
         if (launches4) launches4[i] = n[i];
         if (frame_launches4) frame_launches4[i] = d->class_launches[i];
     }
+    return RT_OK;
+}
+
+int rt_selftest_boxes(uint64_t seed, int64_t n, uint64_t* out8) {
+    if (!out8 || n <= 0) { rtb::set_error("rt_selftest_boxes: bad argument"); return RT_ERR_INVALID; }
+    unsigned long long* d = nullptr;
+    if (cudaMalloc((void**)&d, 8 * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); rtb::set_error("no CUDA device"); return RT_ERR_CUDA; }
+    cudaMemset(d, 0, 8 * sizeof(unsigned long long));
+    rtb::selftest_box_kernel<<<148 * 8, 256>>>((uint32_t)seed, (long long)n, d);
+    const cudaError_t e = cudaMemcpy(out8, d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { rtb::set_error(std::string("rt_selftest_boxes: ") + cudaGetErrorString(e)); return RT_ERR_CUDA; }
+    return RT_OK;
+}
+
+int rt_selftest_cull(rt_scene* scene, uint64_t seed, int32_t rays_per_primitive, uint64_t* out8) {
+    if (!scene || !out8 || rays_per_primitive <= 0) { rtb::set_error("rt_selftest_cull: bad argument"); return RT_ERR_INVALID; }
+    rtb::HostScene& h = *rtb::host_of(scene);
+    int rc = rtb::ensure_uploaded(h, 0, nullptr);
+    if (rc != RT_OK) return rc;
+    rtb::BvhView b;
+    std::memset(&b, 0, sizeof(b));
+    b.prims = h.dev->prims; b.wide = h.dev->wide; b.n_prims = (int)h.dprims.size(); b.use_bvh = 1; b.prune = 1;
+    float span = 1.0f;
+    if (!h.tree.empty())
+        for (int a = 0; a < 3; ++a) span = std::max(span, h.tree[0].box.hi[a] - h.tree[0].box.lo[a]);
+    for (int a = 0; a < 3; ++a) span = std::max(span, 2.0f * std::fabs(h.cam.location[a]));
+    unsigned long long* d = nullptr;
+    if (cudaMalloc((void**)&d, 8 * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); rtb::set_error("cudaMalloc failed"); return RT_ERR_CUDA; }
+    cudaMemset(d, 0, 8 * sizeof(unsigned long long));
+    rtb::selftest_cull_kernel<<<148 * 8, 256>>>(b, (int)h.dwide.size(), rays_per_primitive, (uint32_t)seed, span, d);
+    const cudaError_t e = cudaMemcpy(out8, d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { rtb::set_error(std::string("rt_selftest_cull: ") + cudaGetErrorString(e)); return RT_ERR_CUDA; }
     return RT_OK;
 }
 
