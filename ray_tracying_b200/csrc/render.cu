@@ -1210,7 +1210,9 @@ static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time
     k.hit_prim = d->hit_prim;
     for (int i = 0; i < 2; ++i) { k.recs[i] = d->recs[i]; k.vis[i] = d->vis[i]; }
     k.accum = d->accum; k.lvl = d->lvl; k.totals = d->totals;
-    k.capacity = (int)std::min<long long>(d->capacity, wanted_capacity(batch_units * 32));
+    // all of the allocated queue space, also after a retry with smaller batches (the allocation never
+    // shrinks, so halving the batch really halves the pressure on the queues)
+    k.capacity = (int)std::min<long long>(d->capacity, (1ll << 30));
 
     int launches = 0;
     CUDA_TRY(cudaMemsetAsync(d->lvl, 0, (RT_MAX_DEPTH + 2) * RT_LVL_STRIDE * sizeof(unsigned int), stream));
