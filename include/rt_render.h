@@ -186,7 +186,8 @@ int rt_scene_evict(rt_scene* scene);
 /* CUDA-event timings of the most recent rt_render_device / rt_render call on this scene: the
  * render kernels alone, and everything the call put on the stream. The events are recorded on
  * the launching stream by every call; this getter waits for them, so it can be used after an
- * asynchronous rt_render_device(stats = NULL) without perturbing the timed region. */
+ * asynchronous rt_render_device(stats = NULL) without perturbing the timed region. Returns
+ * RT_ERR_SCENE if that (asynchronous) frame overflowed a ray queue and therefore dropped rays. */
 int rt_scene_last_timing(rt_scene* scene, float* kernel_ms, float* total_ms);
 
 /* Per-kernel-class CUDA-event times of the most recent frame rendered with reserved[1] bit 0 set:

@@ -1456,6 +1456,13 @@ int rt_scene_last_timing(rt_scene* scene, float* kernel_ms, float* total_ms) {
     if (e == cudaSuccess) e = cudaEventElapsedTime(&k, d->ev[1], d->ev[2]);
     if (e == cudaSuccess) e = cudaEventElapsedTime(&t, d->ev[0], d->ev[2]);
     if (e != cudaSuccess) { rtb::set_error(std::string("rt_scene_last_timing: ") + cudaGetErrorString(e)); return RT_ERR_CUDA; }
+    // an asynchronous frame cannot re-render itself when a ray queue overflows: report it here
+    unsigned long long overflow = 0;
+    if (cudaMemcpy(&overflow, d->totals + rtb::T_OVERFLOW, sizeof(overflow), cudaMemcpyDeviceToHost) == cudaSuccess && overflow) {
+        rtb::set_error("the last frame overflowed a ray queue and dropped rays: render once synchronously (stats != NULL) so that the "
+                       "batch size adapts to this scene");
+        return RT_ERR_SCENE;
+    }
     if (kernel_ms) *kernel_ms = k;
     if (total_ms) *total_ms = t;
     return RT_OK;
