@@ -289,6 +289,14 @@ void flatten_scene(HostScene& s) {
         d.q[7] = {bits_f((uint32_t)s.order[k]), 0, 0, 0};
     }
 
+    s.dleafbox.assign((size_t)2 * n, F4{0, 0, 0, 0});
+    for (const TreeNode& t : s.tree) {
+        if (t.left >= 0) continue;
+        for (int k = 0; k < t.count; ++k) {
+            s.dleafbox[2 * (size_t)(t.first + k)] = {t.box.lo[0], t.box.lo[1], t.box.lo[2], 0.0f};
+            s.dleafbox[2 * (size_t)(t.first + k) + 1] = {t.box.hi[0], t.box.hi[1], t.box.hi[2], 0.0f};
+        }
+    }
     s.dwide.clear();
     s.wide_depth = 0;
     if (!s.tree.empty()) {

@@ -282,6 +282,7 @@ RT_DEV bool intersect_prim(const float4* __restrict__ prims, int idx, const Ray&
 struct BvhView {
     const float4* __restrict__ prims;
     const float* __restrict__ wide;  // 32 floats per node
+    const float4* __restrict__ leafbox;  // 2 x float4 per primitive: exact box of its reference leaf
     int n_prims;
     int use_bvh;
     int prune;        // 0: visit everything, exact tests only (the reference's literal traversal)

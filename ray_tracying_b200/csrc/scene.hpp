@@ -110,6 +110,7 @@ struct HostScene {
     // flattened for the device
     std::vector<DPrim> dprims;    // sorted order
     std::vector<DWide> dwide;     // dwide[0] = root (empty when there are no shapes)
+    std::vector<F4> dleafbox;     // per sorted primitive: (lo.xyz, 0), (hi.xyz, 0) of the EXACT box of its reference leaf
     int wide_depth = 0;           // levels of the wide tree (bounds the traversal stack)
     std::vector<DMaterial> dmaterials;
     std::vector<DLight> dlights;
