@@ -72,6 +72,10 @@ namespace rtb {
 // rays / shade records for the statistics.
 enum LevelCounter { L_RAYS = 0, L_RECS = 1, L_WORK_TRACE = 2, L_WORK_SHADOW = 3, L_LIVE_RAYS = 4, L_LIVE_RECS = 5 };
 #define RT_DEAD 0xffffffffu  /* pixel field of a dead ray slot / invalid shade record */
+#ifndef RT_SELF_OCCLUSION_SHADE
+#define RT_SELF_OCCLUSION_SHADE 1
+#endif
+#define RT_VIS_SELF_OCCLUDED (-(1 << 30)) /* visibility counter of a (record, light) pair settled in shade_kernel */
 enum Total { T_PRIMARY = 0, T_SHADOW = 1, T_SECONDARY = 2, T_NODES = 3, T_PRIMS = 4, T_OVERFLOW = 5 };
 
 struct FrameParams {
@@ -568,7 +572,35 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
             o[2] = make_float4(vx, vy, vz, __int_as_float(mat));
             o[3] = make_float4(br, bg, bb, __int_as_float(prim));  // .w: the shape the point lies on (sorted position)
             o[4] = make_float4(__uint_as_float(sample), __uint_as_float(node), 0.0f, 0.0f);
-            for (int l = 0; l < p.n_lights; ++l) p.vis[level & 1][(size_t)rec * p.n_lights + l] = 0;
+            for (int l = 0; l < p.n_lights; ++l) {
+                int v0 = 0;
+#if RT_SELF_OCCLUSION_SHADE
+                // Point lights: a shadow ray that leaves the surface inwards (N . L < 0) is almost always
+                // stopped by the shape it starts on. Decide that HERE, where one thread per hit runs
+                // converged: the exact routine on that shape + the exact box test of its reference leaf
+                // (the reference tests the shape iff that box passes). A hit closer than the light
+                // marks the (record, light) pair as occluded (negative counter) and the shadow kernel
+                // never sees the ray; a miss changes nothing. Same ray arithmetic as ShadowRaysT::load.
+                const float4 l0 = __ldg(p.lights + 2 * l), l1 = __ldg(p.lights + 2 * l + 1);
+                if (l1.w <= 0.0f && p.bvh.prune) {
+                    float lx = l0.x - h.px, ly = l0.y - h.py, lz = l0.z - h.pz;
+                    const float light_dist = sqrtf(dot3(lx, ly, lz, lx, ly, lz));
+                    normalize3(lx, ly, lz);
+                    if (dot3(h.nx, h.ny, h.nz, lx, ly, lz) < 0.0f) {
+                        Ray sr;
+                        sr.ox = h.px + h.nx * 1e-4f; sr.oy = h.py + h.ny * 1e-4f; sr.oz = h.pz + h.nz * 1e-4f;
+                        sr.dx = lx; sr.dy = ly; sr.dz = lz;
+                        sr.time = 0.0f;
+                        Hit sh;
+                        if (intersect_prim<false>(p.bvh.prims, prim, sr, sh) && !(sh.t > light_dist)) {
+                            const float4 blo = __ldg(p.bvh.leafbox + 2 * (size_t)prim), bhi = __ldg(p.bvh.leafbox + 2 * (size_t)prim + 1);
+                            if (!p.bvh.use_bvh || box_exact_call(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, sr)) v0 = RT_VIS_SELF_OCCLUDED;
+                        }
+                    }
+                }
+#endif
+                p.vis[level & 1][(size_t)rec * p.n_lights + l] = v0;
+            }
         }
 
         const bool deeper = level + 1 <= p.max_depth;
@@ -686,6 +718,7 @@ struct ShadowRaysT {
         const int k = (int)(rest % (unsigned int)cnt);
         const float4 r0 = recs[(size_t)rec * 5 + 0];
         if (__float_as_uint(r0.w) == RT_DEAD) return false;
+        if (RT_SELF_OCCLUSION_SHADE && vis[(size_t)rec * p.n_lights + li] < 0) return false;  // settled in shade_kernel
         const float4 r1 = recs[(size_t)rec * 5 + 1];
         float tx = l0.x, ty = l0.y, tz = l0.z;
         const float radius = l1.w;
