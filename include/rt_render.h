@@ -168,6 +168,11 @@ typedef struct rt_bvh_node_dump {
 } rt_bvh_node_dump;
 int rt_scene_dump_bvh(const rt_scene* scene, rt_bvh_node_dump* out, int32_t max_nodes);
 
+/* How the scene loader reads one JSON number (nlohmann semantics: int64 for plain integers, otherwise
+ * the correctly rounded IEEE double of strtod) -- exposed so that the tests can hold the loader's
+ * fast path to strtod bit for bit. */
+int rt_json_number(const char* text, double* value, int32_t* is_integer);
+
 /* The flattened 4-wide device tree (host copy), 32 floats per node, layout in
  * ray_tracying_b200/csrc/scene.hpp (DWide): child boxes as structure of arrays, first child, meta
  * word (valid / gate masks, leaf flag, primitive types), sphere cull coefficient. Writes at most

@@ -106,6 +106,7 @@ SYMBOLS = {
     "rt_render_device": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _VP, _VP, _VP, C.POINTER(RenderStats)]),
     "rt_selftest_boxes": (C.c_int, [C.c_uint64, C.c_int64, C.POINTER(C.c_uint64)]),
     "rt_selftest_cull": (C.c_int, [_VP, C.c_uint64, C.c_int32, C.POINTER(C.c_uint64)]),
+    "rt_json_number": (C.c_int, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "rt_scene_dump_wide": (C.c_int, [_VP, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32)]),
     "rt_scene_last_kernel_times": (C.c_int, [_VP, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "rt_render": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _VP, _VP, C.POINTER(RenderStats)]),

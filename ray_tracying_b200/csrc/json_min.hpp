@@ -20,26 +20,32 @@ namespace jsonmin {
 struct Value;
 using Member = std::pair<std::string, Value>;
 
+// 24 bytes per value: scene files are millions of numbers, so scalars carry no containers; strings,
+// arrays and objects keep theirs in a heap box.
 struct Value {
     enum Kind : uint8_t { Null, Bool, Int, Float, String, Array, Object } kind = Null;
-    bool b = false;
-    int64_t i = 0;
-    double d = 0.0;
-    std::string s;
-    std::vector<Value> arr;
-    std::vector<Member> obj;
+    union {
+        bool b;
+        int64_t i;
+        double d;
+    };
+    struct Box;
+    std::unique_ptr<Box> box;  // String / Array / Object only
+
+    Value() : i(0) {}
+    Value(Value&&) noexcept = default;
+    Value& operator=(Value&&) noexcept = default;
+    Value(const Value&) = delete;
+    Value& operator=(const Value&) = delete;
 
     bool is_object() const { return kind == Object; }
     bool is_array() const { return kind == Array; }
     bool is_number() const { return kind == Int || kind == Float; }
     bool is_string() const { return kind == String; }
 
-    const Value* find(const char* key) const {
-        if (kind != Object) return nullptr;
-        for (const Member& m : obj)
-            if (m.first == key) return &m.second;
-        return nullptr;
-    }
+    inline const std::string& str() const;
+    inline const std::vector<Value>& array() const;
+    inline const Value* find(const char* key) const;
     bool contains(const char* key) const { return find(key) != nullptr; }
     const Value& at(const char* key) const {
         const Value* v = find(key);
@@ -64,11 +70,33 @@ struct Value {
         const Value* v = find(key);
         return v ? v->as_float() : dflt;
     }
-    void as_float3(float out[3]) const {
-        if (kind != Array || arr.size() != 3) throw std::runtime_error("json: expected array of 3 numbers");
-        for (int k = 0; k < 3; ++k) out[k] = arr[k].as_float();
-    }
+    inline void as_float3(float out[3]) const;
 };
+
+struct Value::Box {
+    std::string s;
+    std::vector<Value> arr;
+    std::vector<Member> obj;
+};
+
+inline const std::string& Value::str() const {
+    static const std::string empty;
+    return box ? box->s : empty;
+}
+inline const std::vector<Value>& Value::array() const {
+    static const std::vector<Value> empty;
+    return box ? box->arr : empty;
+}
+inline const Value* Value::find(const char* key) const {
+    if (kind != Object || !box) return nullptr;
+    for (const Member& m : box->obj)
+        if (m.first == key) return &m.second;
+    return nullptr;
+}
+inline void Value::as_float3(float out[3]) const {
+    if (kind != Array || array().size() != 3) throw std::runtime_error("json: expected array of 3 numbers");
+    for (int k = 0; k < 3; ++k) out[k] = box->arr[k].as_float();
+}
 
 class Parser {
 public:
@@ -97,10 +125,10 @@ private:
         switch (*p_) {
             case '{': return parse_object();
             case '[': return parse_array();
-            case '"': { Value v; v.kind = Value::String; v.s = parse_string(); return v; }
+            case '"': { Value v; v.kind = Value::String; v.box.reset(new Value::Box()); v.box->s = parse_string(); return v; }
             case 't': expect_word("true"); { Value v; v.kind = Value::Bool; v.b = true; return v; }
             case 'f': expect_word("false"); { Value v; v.kind = Value::Bool; v.b = false; return v; }
-            case 'n': expect_word("null"); return Value();
+            case 'n': expect_word("null"); { Value v; return v; }
             default: return parse_number();
         }
     }
@@ -111,27 +139,63 @@ private:
         p_ += n;
     }
 
+    // Numbers as nlohmann reads them: integers without fraction / exponent as int64, everything else as
+    // the correctly rounded IEEE double (strtod). Fast path (Clinger): a decimal significand below 2^53
+    // times / over an exactly representable power of ten (<= 1e22) is ONE correctly rounded IEEE
+    // operation on exact operands, i.e. the same double strtod returns; anything else goes to strtod.
     Value parse_number() {
+        static const double pow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                         1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
         const char* start = p_;
-        bool is_float = false;
-        if (p_ != end_ && *p_ == '-') ++p_;
+        bool is_float = false, negative = false;
+        if (p_ != end_ && *p_ == '-') { negative = true; ++p_; }
         if (p_ == end_ || *p_ < '0' || *p_ > '9') fail("invalid number");
-        while (p_ != end_ && *p_ >= '0' && *p_ <= '9') ++p_;
-        if (p_ != end_ && *p_ == '.') { is_float = true; ++p_; while (p_ != end_ && *p_ >= '0' && *p_ <= '9') ++p_; }
+        uint64_t mant = 0;
+        int digits = 0, exp10 = 0;  // significant digits accumulated (leading zeros do not count)
+        while (p_ != end_ && *p_ >= '0' && *p_ <= '9') {
+            if (digits < 19) { mant = mant * 10u + (uint64_t)(*p_ - '0'); if (mant != 0) ++digits; }
+            else { ++exp10; ++digits; }
+            ++p_;
+        }
+        if (p_ != end_ && *p_ == '.') {
+            is_float = true;
+            ++p_;
+            while (p_ != end_ && *p_ >= '0' && *p_ <= '9') {
+                if (digits < 19) { mant = mant * 10u + (uint64_t)(*p_ - '0'); if (mant != 0) ++digits; --exp10; }
+                else ++digits;
+                ++p_;
+            }
+        }
+        bool has_exp = false;
         if (p_ != end_ && (*p_ == 'e' || *p_ == 'E')) {
-            is_float = true; ++p_;
-            if (p_ != end_ && (*p_ == '+' || *p_ == '-')) ++p_;
-            while (p_ != end_ && *p_ >= '0' && *p_ <= '9') ++p_;
+            is_float = true; has_exp = true; ++p_;
+            bool eneg = false;
+            if (p_ != end_ && (*p_ == '+' || *p_ == '-')) { eneg = *p_ == '-'; ++p_; }
+            int e = 0;
+            while (p_ != end_ && *p_ >= '0' && *p_ <= '9') { if (e < 100000) e = e * 10 + (*p_ - '0'); ++p_; }
+            exp10 += eneg ? -e : e;
+        }
+        (void)has_exp;
+        const size_t n = (size_t)(p_ - start);
+        Value v;
+        if (!is_float && n < 19) {
+            v.kind = Value::Int;
+            v.i = negative ? -(int64_t)mant : (int64_t)mant;
+            return v;
+        }
+        v.kind = Value::Float;
+        if (digits <= 19 && mant < (1ull << 53) && exp10 >= -22 && exp10 <= 22) {
+            double x = (double)mant;
+            x = exp10 < 0 ? x / pow10[-exp10] : x * pow10[exp10];
+            v.d = negative ? -x : x;
+            return v;
         }
         char buf[64];
-        size_t n = (size_t)(p_ - start);
         std::string big;
         const char* text;
         if (n < sizeof(buf)) { std::memcpy(buf, start, n); buf[n] = 0; text = buf; }
         else { big.assign(start, n); text = big.c_str(); }
-        Value v;
-        if (!is_float && n < 19) { v.kind = Value::Int; v.i = std::strtoll(text, nullptr, 10); }
-        else { v.kind = Value::Float; v.d = std::strtod(text, nullptr); }
+        v.d = std::strtod(text, nullptr);
         return v;
     }
 
@@ -185,10 +249,11 @@ private:
         ++p_;
         Value v;
         v.kind = Value::Array;
+        v.box.reset(new Value::Box());
         skip_ws();
         if (p_ != end_ && *p_ == ']') { ++p_; return v; }
         while (true) {
-            v.arr.push_back(parse_value());
+            v.box->arr.push_back(parse_value());
             skip_ws();
             if (p_ == end_) fail("unterminated array");
             if (*p_ == ',') { ++p_; continue; }
@@ -202,6 +267,7 @@ private:
         ++p_;
         Value v;
         v.kind = Value::Object;
+        v.box.reset(new Value::Box());
         skip_ws();
         if (p_ != end_ && *p_ == '}') { ++p_; return v; }
         while (true) {
@@ -214,9 +280,9 @@ private:
             Value child = parse_value();
             // nlohmann keeps the LAST duplicate key; emulate by overwriting.
             bool replaced = false;
-            for (Member& m : v.obj)
+            for (Member& m : v.box->obj)
                 if (m.first == key) { m.second = std::move(child); replaced = true; break; }
-            if (!replaced) v.obj.emplace_back(std::move(key), std::move(child));
+            if (!replaced) v.box->obj.emplace_back(std::move(key), std::move(child));
             skip_ws();
             if (p_ == end_) fail("unterminated object");
             if (*p_ == ',') { ++p_; continue; }

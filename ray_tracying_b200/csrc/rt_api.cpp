@@ -6,6 +6,7 @@
 #include <string>
 
 #include "api_internal.hpp"
+#include "json_min.hpp"
 
 namespace rtb {
 thread_local std::string g_last_error;
@@ -126,6 +127,20 @@ int rt_scene_dump_bvh(const rt_scene* scene, rt_bvh_node_dump* out, int32_t max_
         }
     }
     return n;
+}
+
+int rt_json_number(const char* text, double* value, int32_t* is_integer) {
+    if (!text || !value) { rtb::set_error("null argument"); return RT_ERR_INVALID; }
+    try {
+        const jsonmin::Value v = jsonmin::parse(std::string(text));
+        if (!v.is_number()) { rtb::set_error("not a JSON number"); return RT_ERR_INVALID; }
+        *value = v.kind == jsonmin::Value::Int ? (double)v.i : v.d;
+        if (is_integer) *is_integer = v.kind == jsonmin::Value::Int ? 1 : 0;
+        return RT_OK;
+    } catch (const std::exception& e) {
+        rtb::set_error(e.what());
+        return RT_ERR_INVALID;
+    }
 }
 
 int rt_scene_dump_wide(const rt_scene* scene, float* out, int32_t max_nodes, int32_t* depth) {

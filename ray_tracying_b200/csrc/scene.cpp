@@ -13,7 +13,9 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -214,7 +216,7 @@ rt_material_desc parse_material(const Value& mj, TextureTable& textures) {
         m.transparency = mj.value_float("transparency", 0.0f);
         m.refractive_index = mj.value_float("refractive_index", 1.0f);
         if (const Value* tf = mj.find("texture_file")) {
-            if (tf->is_string() && !tf->s.empty()) m.texture = textures.load(tf->s);
+            if (tf->is_string() && !tf->str().empty()) m.texture = textures.load(tf->str());
         }
     } catch (const std::exception& e) {
         std::cerr << "Warning: Error parsing material data: " << e.what() << std::endl;
@@ -229,8 +231,8 @@ void load_camera(const Value& root, rt_camera_desc& c) {
     if (!root.contains("cameras") || !root.contains("render"))
         throw std::runtime_error("JSON file is missing required keys (cameras, render)");
     const Value& cams = root.at("cameras");
-    if (!cams.is_array() || cams.arr.empty()) throw std::runtime_error("'cameras' must be a non-empty array");
-    const Value& cj = cams.arr[0];
+    if (!cams.is_array() || cams.array().empty()) throw std::runtime_error("'cameras' must be a non-empty array");
+    const Value& cj = cams.array()[0];
     c.focal_length = cj.at("focal_length").as_float();
     c.aperture = cj.value_float("aperture", 0.0f);
     c.focus_dist = cj.value_float("focus_dist", 10.0f);
@@ -247,7 +249,7 @@ void load_lights(const Value& root, std::vector<rt_light_desc>& lights) {
     const Value* lj = root.find("lights");
     if (!lj) { std::cerr << "Warning: No valid lights were loaded." << std::endl; return; }
     if (!lj->is_array()) { std::cerr << "Warning: 'lights' key found but is not an array. No lights loaded." << std::endl; return; }
-    for (const Value& l : lj->arr) {
+    for (const Value& l : lj->array()) {
         if (!l.is_object()) { std::cerr << "Warning: Skipping non-object entry in 'lights' array." << std::endl; continue; }
         try {
             if (!l.contains("location") || !l.contains("color") || !l.contains("intensity")) {
@@ -277,7 +279,7 @@ void load_shapes(const Value& root, HostScene& s, MaterialTable& mats, TextureTa
     };
     // 1. spheres (json_loader.cpp:180-234)
     if (const Value* arr = root.find("spheres"); arr && arr->is_array()) {
-        for (const Value& j : arr->arr) {
+        for (const Value& j : arr->array()) {
             if (!j.is_object()) continue;
             try {
                 float t[3], r[3] = {0, 0, 0}, sc[3] = {1, 1, 1}, vel[3] = {0, 0, 0};
@@ -297,7 +299,7 @@ void load_shapes(const Value& root, HostScene& s, MaterialTable& mats, TextureTa
     }
     // 2. cubes (json_loader.cpp:237-278)
     if (const Value* arr = root.find("cubes"); arr && arr->is_array()) {
-        for (const Value& j : arr->arr) {
+        for (const Value& j : arr->array()) {
             if (!j.is_object()) continue;
             try {
                 if (!j.contains("translation") || !j.contains("rotation")) {
@@ -320,7 +322,7 @@ void load_shapes(const Value& root, HostScene& s, MaterialTable& mats, TextureTa
     }
     // 3. rectangles (json_loader.cpp:282-301)
     if (const Value* arr = root.find("rectangles"); arr && arr->is_array()) {
-        for (const Value& j : arr->arr) {
+        for (const Value& j : arr->array()) {
             if (!j.is_object()) continue;
             try {
                 float t[3], r[3], sc[3];
@@ -336,16 +338,16 @@ void load_shapes(const Value& root, HostScene& s, MaterialTable& mats, TextureTa
     }
     // 4. planes (json_loader.cpp:304-332)
     if (const Value* arr = root.find("planes"); arr && arr->is_array()) {
-        for (const Value& j : arr->arr) {
+        for (const Value& j : arr->array()) {
             if (!j.is_object()) continue;
             try {
                 const Value* cj = j.find("corners");
-                if (!cj || !cj->is_array() || cj->arr.size() != 4) {
+                if (!cj || !cj->is_array() || cj->array().size() != 4) {
                     std::cerr << "Warning: Skipping invalid plane definition." << std::endl;
                     continue;
                 }
                 float corners[12];
-                for (int k = 0; k < 4; ++k) cj->arr[k].as_float3(corners + 3 * k);
+                for (int k = 0; k < 4; ++k) cj->array()[k].as_float3(corners + 3 * k);
                 int mat = material_of(j);
                 s.prims.push_back(make_prim(RT_PLANE, mat, zero3, zero3, zero3, zero3, corners));
             } catch (const std::exception& e) {
@@ -384,19 +386,36 @@ void finalize_scene(HostScene& s) {
 }
 
 void load_scene_json(const std::string& path, const std::string& texture_dir, HostScene& s) {
-    std::ifstream f(path, std::ios::binary);
-    if (!f.is_open()) throw std::runtime_error("Could not open JSON file: " + path);
-    std::stringstream buf;
-    buf << f.rdbuf();
-    const std::string text = buf.str();
+    const bool timing = std::getenv("RT_B200_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const auto t0 = now();
+    std::string text;
+    {
+        std::FILE* f = std::fopen(path.c_str(), "rb");
+        if (!f) throw std::runtime_error("Could not open JSON file: " + path);
+        std::fseek(f, 0, SEEK_END);
+        const long size = std::ftell(f);
+        std::fseek(f, 0, SEEK_SET);
+        text.resize(size > 0 ? (size_t)size : 0);
+        const size_t got = text.empty() ? 0 : std::fread(&text[0], 1, text.size(), f);
+        std::fclose(f);
+        text.resize(got);
+    }
+    const auto t1 = now();
     Value root = jsonmin::parse(text);
+    const auto t2 = now();
     if (!root.is_object()) throw std::runtime_error("scene root must be a JSON object");
     load_camera(root, s.cam);
     load_lights(root, s.lights);
     MaterialTable mats(s.materials);
     TextureTable textures{s, texture_dir.empty() ? std::string("../../Textures") : texture_dir, {}};
     load_shapes(root, s, mats, textures);
+    const auto t3 = now();
     finalize_scene(s);
+    if (timing)
+        std::fprintf(stderr, "[rt_b200] load %s: read %.3f s, parse %.3f s, shapes %.3f s, bvh %.3f s, flatten %.3f s\n", path.c_str(),
+                     secs(t0, t1), secs(t1, t2), secs(t2, t3), s.build_seconds, secs(t3, now()) - s.build_seconds);
 }
 
 void create_scene_from_desc(const rt_scene_desc& d, HostScene& s) {

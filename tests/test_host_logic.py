@@ -238,3 +238,38 @@ def test_wide_tree_encodes_the_reference_tree(rt, name):
     visit(0, 1, 0)
     assert seen_leaves == set(ref_leaves), "every reference leaf is reachable exactly once"
     assert max_sp[0] <= 3 * (depth - 1) + 1
+
+
+def test_json_numbers_are_strtod_exact(rt):
+    """The loader's number fast path (significand < 2^53 times / over a power of ten <= 1e22) must return
+    the double Python's float() (= correctly rounded strtod) returns, bit for bit; integers stay integers."""
+    import ctypes as C
+    import random
+    from ray_tracying_b200._lib import lib
+    rng = random.Random(7)
+    cases = ["0", "-0", "0.0", "-0.0", "1", "-17", "123456789012345678", "1234567890123456789", "0.1", "0.30000000000000004",
+             "1e22", "1e23", "1E-22", "1e-23", "9007199254740991.0", "9007199254740993.0", "4.35", "0.000001", "1.7976931348623157e308",
+             "5e-324", "2.2250738585072011e-308", "123456789012345678901234567890.5", "0.1000000000000000055511151231257827",
+             "3.14159265358979323846264338327950288", "-2.5e-5", "1e0", "12.0e+3", "8.0E3", "0.5000"]
+    for _ in range(20000):
+        digits = rng.randint(1, 22)
+        m = str(rng.randint(0, 10 ** digits - 1))
+        cut = rng.randint(0, len(m))
+        txt = (m[:cut] or "0") + ("." + m[cut:] if cut < len(m) else "")
+        if rng.random() < 0.3:
+            txt += "e" + str(rng.randint(-30, 30))
+        if rng.random() < 0.5:
+            txt = "-" + txt
+        if txt.lstrip("-").startswith("0") and len(txt.lstrip("-")) > 1 and txt.lstrip("-")[1] != "." and txt.lstrip("-")[1] not in "eE":
+            txt = txt.replace("0", "1", 1)  # JSON forbids leading zeros
+        cases.append(txt)
+    for txt in cases:
+        val, is_int = C.c_double(), C.c_int32()
+        assert lib.rt_json_number(txt.encode(), C.byref(val), C.byref(is_int)) == 0, txt
+        plain_int = txt.lstrip("-").isdigit() and len(txt) < 19
+        assert bool(is_int.value) == plain_int, txt
+        if plain_int:  # nlohmann: a plain integer is an int64 ("-0" is the integer 0)
+            assert val.value == float(int(txt)), txt
+        else:
+            want = float(txt)
+            assert np.float64(val.value).view(np.uint64) == np.float64(want).view(np.uint64), (txt, val.value, want)
