@@ -250,6 +250,7 @@ private:
         Value v;
         v.kind = Value::Array;
         v.box.reset(new Value::Box());
+        v.box->arr.reserve(4);  // most arrays of a scene file are 3-vectors
         skip_ws();
         if (p_ != end_ && *p_ == ']') { ++p_; return v; }
         while (true) {
@@ -268,6 +269,7 @@ private:
         Value v;
         v.kind = Value::Object;
         v.box.reset(new Value::Box());
+        v.box->obj.reserve(8);
         skip_ws();
         if (p_ != end_ && *p_ == '}') { ++p_; return v; }
         while (true) {
