@@ -5,23 +5,28 @@
 
 A step = one frame of the workload: per-pixel ray generation, BVH traversal, ray-primitive
 intersection, Blinn-Phong shading with shadow/reflection/refraction rays (the reference's frame
-loop, raytracer.cpp:433-476). With N > 1 (torchrun, one rank per GPU) the frame is sharded by
-interleaved screen tiles, scene and BVH replicated, and assembled with one all_gather at frame
-end. Rays = get_intersection calls (primary + shadow + reflection + refraction).
+loop, raytracer.cpp:433-476). Rays = get_intersection calls (primary + shadow + reflection +
+refraction). The headline workload is BASELINE.json's configs[2] -- the one its target is stated on:
+1M-triangle soup, 1920x1080, 64 spp antialiasing, 16-sample area-light soft shadows -- at every N; the
+same JSON line carries configs[1] (100k mixed shapes, 1 spp, depth 5: a 5 ms frame) as `secondary`.
 
-Workloads (BASELINE.json configs; the default is configs[1]):
-    mixed100k : 100k-shape mixed scene (spheres/ellipsoids, cubes incl. rod-like ones, rectangles,
-                plane quads = 2 triangles each), 1920x1080, 1 spp, Whitted depth 5       [configs[1]]
-    soup1m    : 1M-triangle soup (500k plane quads), 1080p, 64 spp, 16-sample area light  [configs[2]]
-    glossy250k: 250k-triangle glossy scene, 3840x2160, 100 spp, depth 8                   [configs[3]]
-    dof4m     : 4M-triangle scene, thin lens + motion blur, 3840x2160, 256 spp            [configs[4]]
-    ascii     : the reference's own ASCII/scene.json, 1 spp                               [configs[0]]
+  value : device-timed. With N > 1 (torchrun, one rank per GPU) the frame is sharded by interleaved
+          screen tiles, scene and BVH replicated, no traffic between GPUs inside the render loop, one
+          NCCL all_gather of the packed tiles at frame end; max over ranks of the CUDA-event time.
+  e2e   : the same frame through the C ABI with HOST buffers, every step: scene evicted, H2D copy of
+          the scene from page-locked memory, render, D2H copy of the frame into page-locked memory.
+          N = 1: rt_render. N > 1: rt_render_multi -- ONE process (rank 0) drives the N GPUs, each GPU
+          copies its own packed tiles to the host, no NCCL; the other ranks wait.
+  roofline : the traversal kernels against a MEASURED traversal ceiling of this chip (rt_traversal_peak:
+          the loop's node step with fully converged warps on L1-resident nodes), in box tests per second.
 
 --impl reference times the reference's OWN CPU code (oracle/_ref/ref_driver = the unmodified
 reference sources behind a small driver) on a bounded sample of the same workload with every host
-core (one process per core over row bands: the reference BVH object is not thread-safe).
+core (one process per core over windows spread over the frame: the reference BVH object is not
+thread-safe). Nothing of the product library is loaded in that arm.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -34,45 +39,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CACHE = os.environ.get("RT_BENCH_CACHE", "/tmp/rt_b200_bench")
+from ray_tracying_b200 import workloads  # noqa: E402  (pure Python: does not load librt_b200.so)
 
-WORKLOADS = {
-    # name: (generator kwargs, render kwargs, description)
-    "mixed100k": dict(gen=("mixed_scene", dict(n_shapes=100000, seed=1, resolution=(1920, 1080), extent=30.0, height=6.0)),
-                      render=dict(use_bvh=True, n_samples_sqrt=1, light_samples=1, max_depth=5),
-                      desc="configs[1]: 100k-shape mixed scene, 1920x1080, 1 spp, Whitted depth 5"),
-    "soup1m": dict(gen=("quad_soup", dict(n_triangles=1000000, seed=2, resolution=(1920, 1080), extent=40.0, height=8.0,
-                                          light_radius=2.0, n_lights=1)),
-                   render=dict(use_bvh=True, n_samples_sqrt=8, light_samples=16, max_depth=10),
-                   desc="configs[2]: 1M-triangle soup (500k quads), 1920x1080, 64 spp, 16-sample area light"),
-    "glossy250k": dict(gen=("quad_soup", dict(n_triangles=250000, seed=3, resolution=(3840, 2160), extent=25.0, height=6.0,
-                                              glossy=True, n_lights=2)),
-                       render=dict(use_bvh=True, n_samples_sqrt=10, light_samples=1, max_depth=8),
-                       desc="configs[3]: 250k-triangle glossy scene, 3840x2160, 100 spp, depth 8"),
-    "dof4m": dict(gen=("quad_soup", dict(n_triangles=4000000, seed=4, resolution=(3840, 2160), extent=60.0, height=10.0,
-                                         aperture=0.8, n_moving_spheres=64, n_lights=2)),
-                  render=dict(use_bvh=True, n_samples_sqrt=16, light_samples=1, max_depth=10),
-                  desc="configs[4]: 4M-triangle scene, thin-lens DOF + motion blur, 3840x2160, 256 spp"),
-    "ascii": dict(gen=("ascii", {}), render=dict(use_bvh=True, n_samples_sqrt=1, light_samples=1, max_depth=10),
-                  desc="configs[0]: the reference's ASCII/scene.json, 1920x1080, 1 spp"),
-}
-
-
-def scene_path_for(name: str) -> str:
-    os.makedirs(CACHE, exist_ok=True)
-    if name == "ascii":
-        return os.path.join(ROOT, "tests", "golden", "ascii_scene.json")
-    path = os.path.join(CACHE, name + ".json")
-    if not os.path.exists(path):
-        from ray_tracying_b200 import scenes
-        fn, kw = WORKLOADS[name]["gen"]
-        t0 = time.time()
-        sc = getattr(scenes, fn)(**kw)
-        scenes.write_scene(sc, path + ".tmp")
-        os.replace(path + ".tmp", path)
-        print(f"[bench] generated {name}: {scenes.shape_count(sc)} shapes, {os.path.getsize(path) / 1e6:.1f} MB in {time.time() - t0:.1f}s",
-              file=sys.stderr)
-    return path
+WORKLOADS = workloads.WORKLOADS
+scene_path_for = workloads.scene_path_for
 
 
 # ------------------------------------------------------------------------------------------------
@@ -119,68 +89,77 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# the reference on the host cores (oracle/_ref/ref_driver; oracle port only to COUNT rays)
+# the reference on the host cores (oracle/_ref/ref_driver; oracle port only to size the sample and COUNT rays)
 # ------------------------------------------------------------------------------------------------
-def reference_sample(scene_path: str, render: dict, repeats: int, target_seconds: float = 4.0):
-    """Runs the unmodified reference on row bands spread over the frame, one process per host core.
-    Returns dict(seconds=[per repeat, max over processes], rays, rows, cores, kind)."""
+def reference_sample(name: str, scene_path: str, render: dict, repeats: int, target_seconds: float = 4.0):
+    """Runs the unmodified reference on windows spread over the frame, one process per host core, ONE
+    invocation per process (the scene load + BVH build of the reference takes ~40 s for the 1M-triangle
+    scene). Returns dict(seconds=[per repeat, max over processes], rays, pixels, cores, kind, ...)."""
+    from oracle import scene_io
     from oracle.oracle import REF_DRIVER, OracleScene, RefDriver
-    with open(scene_path) as f:
-        scene = json.load(f)
-    width, height = scene["render"]["resolution_x"], scene["render"]["resolution_y"]
-    cores = os.cpu_count() or 1
-    procs = max(1, min(cores, height))
+    sc = workloads.scene_dict(name)
+    width, height = sc["render"]["resolution_x"], sc["render"]["resolution_y"]
     spp = max(1, render["n_samples_sqrt"]) ** 2 if render["n_samples_sqrt"] > 1 else 1
     kind = "reference" if RefDriver.available() else "port"
+    oracle = OracleScene(*scene_io.scene_arrays(sc, os.path.join(ROOT, "tests", "golden")))
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, height))
+    if kind == "reference":
+        # nlohmann's DOM of the scene file costs ~12x its size per process: keep the processes within half the RAM
+        try:
+            import psutil
+            procs = max(1, min(procs, int(0.5 * psutil.virtual_memory().available / max(1.0, 12.0 * os.path.getsize(scene_path)))))
+        except Exception:
+            pass
 
-    def bands(rows_per_proc):
+    # rays per pixel from a probe with the port, then a window per process worth ~target_seconds of one core
+    # (0.13 Mrays/s per core is what the reference does on this class of host; the time is MEASURED below)
+    probe_rows = (int(0.55 * height), int(0.55 * height) + 1)
+    probe_cols = (int(0.4 * width), int(0.4 * width) + 64)
+    probe = oracle.render(rows=probe_rows, cols=probe_cols, seed=1, **render)
+    rays_per_px = max(1.0, sum(probe["rays"]) / 64.0)
+    target_px = max(8, int(0.13e6 * target_seconds * (1.0 if kind == "reference" else cores) / rays_per_px))
+    rows = max(1, min(height // procs, target_px // width))
+    cols = width if target_px >= width else max(8, target_px)
+    wins = []
+    for i in range(procs):
         stride = height / procs
-        out = []
-        for i in range(procs):
-            y0 = min(height - rows_per_proc, int(i * stride + 0.5 * max(0.0, stride - rows_per_proc)))
-            out.append((y0, y0 + rows_per_proc))
-        return out
+        y0 = min(height - rows, int(i * stride + 0.5 * max(0.0, stride - rows)))
+        x0 = 0 if cols >= width else int((i * 0.618034) % 1.0 * (width - cols))  # golden-ratio spread over the columns
+        wins.append((x0, y0, x0 + cols, y0 + rows))
 
-    def run_ref(rows_list, reps):
-        cmds = []
-        for (y0, y1) in rows_list:
-            cmds.append([REF_DRIVER, "--scene", scene_path, "--mode", "render", "--bvh", str(int(render["use_bvh"])),
-                         "--s", str(render["n_samples_sqrt"]), "--light-samples", str(render["light_samples"]),
-                         "--depth", str(render["max_depth"]), "--seed", "1", "--rows", str(y0), str(y1), "--repeat", str(reps)])
+    if kind == "reference":
+        cmds = [[REF_DRIVER, "--scene", scene_path, "--mode", "render", "--bvh", str(int(render["use_bvh"])),
+                 "--s", str(render["n_samples_sqrt"]), "--light-samples", str(render["light_samples"]),
+                 "--depth", str(render["max_depth"]), "--seed", "1", "--rows", str(y0), str(y1), "--cols", str(x0), str(x1),
+                 "--repeat", str(repeats)] for (x0, y0, x1, y1) in wins]
         ps = [subprocess.Popen(c, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for c in cmds]
         per_proc = []
         for p in ps:
             out, _ = p.communicate()
             if p.returncode != 0:
                 raise RuntimeError("ref_driver failed")
-            info = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
-            per_proc.append(info["all_seconds"])
-        return [max(pp[i] for pp in per_proc) for i in range(reps)], per_proc
-
-    oracle = OracleScene.from_dict(scene, os.path.join(ROOT, "tests", "golden"))
-
-    def run_port(rows_list, reps):
-        secs = []
-        for _ in range(reps):
+            per_proc.append(json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])["all_seconds"])
+        seconds = [max(pp[i] for pp in per_proc) for i in range(repeats)]
+        used = procs
+    else:
+        seconds = []
+        for _ in range(repeats):
             t0 = time.perf_counter()
-            for rows in rows_list:
-                oracle.render(rows=rows, threads=cores, seed=1, **render)
-            secs.append(time.perf_counter() - t0)
-        return secs, None
-
-    run = run_ref if kind == "reference" else run_port
-    # calibrate: one row per process, then scale the band to ~target_seconds per repeat
-    cal, _ = run(bands(1), 1)
-    rows_per_proc = int(max(1, min(height // procs, round(target_seconds / max(cal[0], 1e-3)))))
-    rows_list = bands(rows_per_proc)
-    seconds, _ = run(rows_list, repeats)
-    # ray count of exactly these rows from the oracle port (identical for deterministic workloads,
-    # statistically equal for stochastic ones)
-    rays = 0
-    for rows in rows_list:
-        rays += sum(oracle.render(rows=rows, threads=cores, seed=1, **render)["rays"])
-    return {"seconds": seconds, "rays": rays, "rows": rows_per_proc * procs, "cores": procs if kind == "reference" else cores,
+            for (x0, y0, x1, y1) in wins:
+                oracle.render(rows=(y0, y1), cols=(x0, x1), threads=cores, seed=1, **render)
+            seconds.append(time.perf_counter() - t0)
+        used = cores
+    # ray count of exactly these windows from the oracle port (identical for deterministic workloads,
+    # statistically equal for stochastic ones: the reference draws from mt19937, the port from Philox)
+    rays = sum(sum(oracle.render(rows=(y0, y1), cols=(x0, x1), threads=cores, seed=1, **render)["rays"]) for (x0, y0, x1, y1) in wins)
+    return {"seconds": seconds, "rays": rays, "pixels": rows * cols * procs, "window": [cols, rows], "cores": used,
             "kind": kind, "width": width, "height": height, "spp": spp}
+
+
+def sample_text(res: dict) -> str:
+    return (f"{res['cores']} windows of {res['window'][0]} x {res['window'][1]} px spread over the {res['width']} x {res['height']} frame "
+            f"({res['pixels']} px x {res['spp']} spp, {res['rays']} rays per step), one process per core")
 
 
 def run_reference_arm(args, wl):
@@ -188,19 +167,18 @@ def run_reference_arm(args, wl):
     if rank != 0:
         return
     path = scene_path_for(args.workload)
-    # bounded: the whole run (warm-up + steps samples, each on every host core) stays within ~2 minutes
-    res = reference_sample(path, wl["render"], args.warmup + args.steps, target_seconds=max(0.5, min(4.0, 100.0 / (args.warmup + args.steps))))
+    # bounded: the whole run (warm-up + steps samples, each on every host core) stays within a few minutes
+    res = reference_sample(args.workload, path, wl["render"], args.warmup + args.steps,
+                           target_seconds=max(0.5, min(4.0, 100.0 / (args.warmup + args.steps))))
     secs = res["seconds"][args.warmup:]
     ms = float(np.mean(secs)) * 1e3
     value = res["rays"] / (ms * 1e-3) / 1e6
-    sample = (f"{res['rows']} of {res['height']} rows x {res['width']} px x {res['spp']} spp per step, "
-              f"row bands spread over the frame, one process per core")
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "name": args.workload, **wl["render"], "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": res["cores"], "kind": res["kind"], "sample": sample},
+        "config": {"workload": wl["desc"], "name": args.workload, **wl["render"], "sample": sample_text(res)},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": res["cores"], "kind": res["kind"], "sample": sample_text(res)},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "rays_per_step": res["rays"],
     }
@@ -210,42 +188,75 @@ def run_reference_arm(args, wl):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args, wl):
-    import torch
-    import torch.distributed as dist
+def kernel_source_tag() -> str:
+    """Identifies the kernel sources a profile under profiles/ was captured with."""
+    h = hashlib.sha256()
+    for f in ("render.cu", "rt_device.cuh", "philox.cuh", "bvh.cpp"):
+        with open(os.path.join(ROOT, "ray_tracying_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
+
+class Ranks:
+    """torch.distributed plumbing of one bench process (rank)."""
+
+    def __init__(self, gpus: int):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world == 1 and gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torchrun (one rank per GPU)")
+        torch.cuda.set_device(self.local_rank)
+        self.host_group = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            # a HOST barrier (gloo): ranks that wait for rank 0's rt_render_multi must not spin on their GPUs
+            self.host_group = dist.new_group(backend="gloo")
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def host_barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.host_group)
+
+    def max_(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def sum_(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.int64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return [int(x) for x in t.tolist()]
+
+
+def measure(rk: Ranks, name: str, steps: int, warmup: int, full: bool, tile=(32, 32), tile_block: int = 0) -> dict:
+    """One workload on this job's ranks. full = also the roofline leg, the traversal ceiling and the clocks."""
     import ray_tracying_b200 as rt
     from ray_tracying_b200 import dist as rdist
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus N > 1 must be launched with torchrun (one rank per GPU)")
-    if rt.device_count() < 1:
-        raise SystemExit("bench.py needs a CUDA device: the render path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    torch = rk.torch
+    wl = WORKLOADS[name]
+    R = wl["render"]
+    world, rank = rk.world, rk.rank
 
     if rank == 0:
-        path = scene_path_for(args.workload)
-    barrier()
-    path = scene_path_for(args.workload)
-
+        scene_path_for(name)
+    rk.host_barrier()
+    path = scene_path_for(name)
     t0 = time.perf_counter()
     scene = rt.Scene.from_json(path, os.path.join(ROOT, "tests", "golden"))
     load_s = time.perf_counter() - t0
     width, height = scene.resolution
-    tile = (32, 32)
-    R = wl["render"]
-    params = rt.make_params(rank=rank, world=world, tile=tile, seed=1, **R)
+    common = dict(tile=tile, tile_block=tile_block, seed=1, **R)
     h2d_bytes = scene.upload()
 
     rgb = torch.zeros((height, width, 3), dtype=torch.uint8, device="cuda")
@@ -253,164 +264,193 @@ def run_ours(args, wl):
     stream = torch.cuda.current_stream()
 
     # one untimed pass with counters: rays per step and the traversal work (for the roofline)
-    st = scene.render_device(rt.make_params(rank=rank, world=world, tile=tile, seed=1, collect_stats=True, **R), rgb.data_ptr(),
-                             0, 0, stream.cuda_stream)
-    counts = torch.tensor([st.rays, st.primary_rays, st.shadow_rays, st.secondary_rays, st.node_visits, st.prim_tests],
-                          dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(counts)
-    rays, n_primary, n_shadow, n_secondary, node_visits, prim_tests = (int(x) for x in counts.tolist())
-    launches_per_step = int(st.launches)
+    st = scene.render_device(rt.make_params(rank=rank, world=world, collect_stats=True, **common), rgb.data_ptr(), 0, 0, stream.cuda_stream)
+    rays, n_primary, n_shadow, n_secondary, box_tests, prim_tests = rk.sum_(
+        [st.rays, st.primary_rays, st.shadow_rays, st.secondary_rays, st.node_visits, st.prim_tests])
+    my_box_tests = st.node_visits
 
-    params = rt.make_params(rank=rank, world=world, tile=tile, seed=1, **R)
-    # roofline leg: the same frames with the launches serialised on one stream and CUDA events
-    # around every trace / shadow / shade / light launch, so each kernel's duration is its own
-    # (in the headline steps shadow/light of a level overlap trace/shade of the next level)
-    params_serial = rt.make_params(rank=rank, world=world, tile=tile, seed=1, time_kernels=True, serial=True, **R)
+    params = rt.make_params(rank=rank, world=world, **common)
 
     def one_step():
         scene.render_device(params, rgb.data_ptr(), 0, 0, stream.cuda_stream, sync_stats=False)
-        return rdist.gather_frame(rgb, width, height, tile, rank, world) if world > 1 else rgb
+        return rdist.gather_frame(rgb, width, height, tile, rank, world, block=tile_block) if world > 1 else rgb
 
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(rk.local_rank)
     step_ms, kernel_ms = [], []
-    for i in range(args.warmup + args.steps):
+    launches0 = scene.launch_count()
+    for i in range(warmup + steps):
         flush.zero_()  # evict the scene from L2 between iterations
-        if i == args.warmup and rank == 0:
-            clocks.start()
-        barrier()
+        if i == warmup:
+            launches0 = scene.launch_count()
+            if rank == 0 and full:
+                clocks.start()
+        rk.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         one_step()
         e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1), scene.last_timing()[0]], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if i >= args.warmup:
-            step_ms.append(float(t[0]))
-            kernel_ms.append(float(t[1]))
-    trav_ms, serial_ms, trav_launches, class_ms = [], [], 0, {}
-    for i in range(max(3, min(args.steps, 10))):
-        flush.zero_()
-        barrier()
-        scene.render_device(params_serial, rgb.data_ptr(), 0, 0, stream.cuda_stream, sync_stats=False)
-        barrier()
-        kt = scene.last_kernel_times()
-        t = torch.tensor([kt["trace"][0] + kt["shadow"][0], scene.last_timing()[0]], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        trav_ms.append(float(t[0]))
-        serial_ms.append(float(t[1]))
-        trav_launches = kt["trace"][1] + kt["shadow"][1]
-        trav_frame_launches = kt["trace"][2] + kt["shadow"][2]
-        for k, (ms_k, n_k, tot_k) in kt.items():
-            class_ms.setdefault(k, []).append(ms_k * tot_k / max(n_k, 1))  # scaled to the whole frame
-    clock_info = clocks.stop() if rank == 0 else {}
+        rk.barrier()
+        t = rk.max_([e0.elapsed_time(e1), scene.last_timing()[0]])
+        if i >= warmup:
+            step_ms.append(t[0])
+            kernel_ms.append(t[1])
+    launches = rk.sum_([scene.launch_count() - launches0])[0]  # kernels of librt_b200.so launched inside the timed region, all ranks
+    clock_info = clocks.stop() if (rank == 0 and full) else {}
     ms = float(np.mean(step_ms))
-    k_ms = float(np.mean(kernel_ms))
-    value = rays / (ms * 1e-3) / 1e6
+    out = {
+        "name": name, "desc": wl["desc"], "render": R, "resolution": [width, height], "shapes": scene.counts()["shapes"],
+        "rays": rays, "ray_classes": {"primary": n_primary, "shadow": n_shadow, "secondary": n_secondary},
+        "ms_per_step": ms, "value": rays / (ms * 1e-3) / 1e6, "kernel_ms_per_step": float(np.mean(kernel_ms)),
+        "gpu_launches": launches, "load_s": load_s, "clocks": clock_info, "h2d_bytes": int(h2d_bytes),
+        "box_tests": box_tests, "prim_tests": prim_tests,
+    }
 
-    # end to end through the C ABI with HOST buffers, every step: H2D copy of the scene from
+    # roofline leg: the same frames with the launches serialised on one stream and CUDA events around EVERY
+    # trace / shadow / shade / light launch, so each kernel's duration is its own (in the headline steps
+    # shadow/light of a level overlap trace/shade of the next level)
+    if full:
+        params_serial = rt.make_params(rank=rank, world=world, time_kernels=True, serial=True, **common)
+        trav_ms, serial_ms, class_ms, n_trav = [], [], {}, 0
+        for i in range(max(2, min(steps, 5))):
+            flush.zero_()
+            rk.barrier()
+            scene.render_device(params_serial, rgb.data_ptr(), 0, 0, stream.cuda_stream, sync_stats=False)
+            rk.barrier()
+            kt = scene.last_kernel_times()
+            for cls, (ms_k, n_timed, n_all) in kt.items():
+                assert n_timed == n_all, "every launch of the frame is timed"
+                class_ms.setdefault(cls, []).append(ms_k)
+            # this rank's box-test rate is what the ceiling bounds; ranks differ little (interleaved tiles)
+            trav_ms.append(kt["trace"][0] + kt["shadow"][0])
+            serial_ms.append(scene.last_timing()[0])
+            n_trav = kt["trace"][2] + kt["shadow"][2]
+        trav = float(np.mean(trav_ms))
+        peak_closest, _ = scene.traversal_peak(any_hit=False)
+        peak_any, _ = scene.traversal_peak(any_hit=True)
+        out["roofline_leg"] = {"trav_ms": trav, "serial_ms": float(np.mean(serial_ms)), "n_trav_launches": n_trav,
+                               "class_ms": {k: float(np.mean(v)) for k, v in class_ms.items()},
+                               "my_box_tests": my_box_tests, "peak_closest": peak_closest, "peak_any": peak_any}
+
+    # end to end through the C ABI with HOST buffers, every step: scene evicted -> H2D copy of the scene from
     # page-locked host memory, render, D2H copy of the frame into page-locked host memory.
-    #   1 GPU : rt_render() does all of it (Scene.render_into);
-    #   N GPUs: upload + rt_render_device + frame-end all_gather + D2H of the assembled frame.
+    #   1 GPU : rt_render (Scene.render_into);
+    #   N GPUs: rt_render_multi driven by rank 0 alone (one process, N devices); the other ranks wait on the host.
     host_frame = torch.empty((height, width, 3), dtype=torch.uint8, pin_memory=True)
-    p_e2e = rt.make_params(rank=rank, world=world, tile=tile, seed=1, **R)
+    p_e2e = rt.make_params(**common)
     e2e_s = []
-    e2e_warm = max(1, min(args.warmup, 2))
-    for i in range(e2e_warm + args.steps):
-        flush.zero_()
-        scene.evict()
-        barrier()
-        w0 = time.perf_counter()
-        if world == 1:
-            scene.render_into(p_e2e, host_frame.data_ptr())
-        else:
-            scene.upload()
-            scene.render_device(p_e2e, rgb.data_ptr(), 0, 0, stream.cuda_stream, sync_stats=False)
-            frame = rdist.gather_frame(rgb, width, height, tile, rank, world)
-            host_frame.copy_(frame, non_blocking=False)
-            torch.cuda.synchronize()
-        w1 = time.perf_counter()
-        t = torch.tensor([w1 - w0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if i >= e2e_warm:
-            e2e_s.append(float(t[0]))
-    e2e_value = rays / float(np.mean(e2e_s)) / 1e6
+    e2e_warm = max(1, min(warmup, 2))
+    del flush
+    torch.cuda.empty_cache()
+    rk.host_barrier()
+    if rank == 0:
+        flush0 = [torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{d}") for d in range(world)]
+        for i in range(e2e_warm + steps):
+            for f in flush0:
+                f.zero_()
+            scene.evict()
+            for d in range(world):
+                torch.cuda.synchronize(d)
+            w0 = time.perf_counter()
+            if world == 1:
+                scene.render_into(p_e2e, host_frame.data_ptr())
+            else:
+                scene.render_multi_into(p_e2e, world, host_frame.data_ptr())
+            w1 = time.perf_counter()
+            if i >= e2e_warm:
+                e2e_s.append(w1 - w0)
+        del flush0
+    rk.host_barrier()
+    if rank == 0:
+        e2e_ms = float(np.mean(e2e_s)) * 1e3
+        out["e2e"] = {"value": rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d_bytes) * world,
+                      "d2h_bytes_per_step": int(width * height * 3), "ms_per_step": e2e_ms,
+                      "path": "rt_render (C ABI, page-locked host buffers)" if world == 1 else
+                              f"rt_render_multi (C ABI, one process driving {world} GPUs, page-locked host buffers, no NCCL)"}
+    scene.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args, wl):
+    import ray_tracying_b200 as rt
+    if rt.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the render path has no CPU fallback")
+    rk = Ranks(args.gpus)
+    world, rank = rk.world, rk.rank
+    tile = (32, 32)
+    head = measure(rk, args.workload, args.steps, args.warmup, full=True, tile=tile, tile_block=args.tile_block)
+    second = None
+    if args.secondary and args.secondary != args.workload:
+        second = measure(rk, args.secondary, args.steps, args.warmup, full=True, tile=tile, tile_block=args.tile_block)
 
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            with open(peaks_path) as f:
-                peak, peak_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
-        else:
-            peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-        # Dominant kernel = the traversal loop (trace_kernel and shadow_kernel are the two
-        # instantiations of wave_loop). Algorithmic bytes: every box test reads
-        # one child box (32 B of a 128 B node), every primitive test the 64 B head of a primitive
-        # record, every ray its 32 B origin/direction and writes a 4 B result.
-        alg_bytes = node_visits * 32 + prim_tests * 64 + rays * 36
-        n_launch = max(1, trav_frame_launches)
-        # frames with many batches time the first 512 launches only: scale to the frame's launch count
-        trav = float(np.mean(trav_ms)) * n_launch / max(1, trav_launches)
-        achieved = alg_bytes / world / (trav * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
+        tag = kernel_source_tag()
+        captured = {}
+        tp = os.path.join(ROOT, "profiles", "traffic_r2.json")
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get(args.workload)
-        # what actually bounds the loop (committed ncu capture of this workload, not measured in this run):
-        # issue-slot utilisation and active lanes per instruction of the traversal kernels
-        ncu_note = None
-        kp = os.path.join(ROOT, "profiles", "ncu_key_metrics.json")
-        if os.path.exists(kp) and args.workload == "mixed100k":
-            with open(kp) as f:
-                km = json.load(f)
-            ncu_note = {"source": km["source"],
-                        "kernels": {k.replace("void ", ""): {m: round(v[0][m], 2) for m in ("issue_slot_pct", "lanes_per_instruction", "l1_hit_pct", "warps_active_pct")}
-                                    for k, v in km["kernels"].items()}}
+                captured = json.load(f)
+
+        def roofline(m):
+            # Dominant kernels = the traversal loops (trace_kernel / shadow_kernel / their packet flavours): one
+            # number for all of them, box tests per second, against the measured ceiling of the loop's node step.
+            leg = m["roofline_leg"]
+            achieved = leg["my_box_tests"] / (leg["trav_ms"] * 1e-3) / 1e9
+            peak = max(leg["peak_closest"], leg["peak_any"]) / 1e9
+            cap = captured.get(m["name"]) if captured.get("kernel_source_tag") == tag else None
+            return {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "Gbox-tests/s", "frac": achieved / peak,
+                    "traffic": cap["dram_bytes_per_launch"] if cap else None,
+                    "traffic_source": (captured.get("source") if cap else "no ncu capture of these kernel sources under profiles/"),
+                    "peak_source": "rt_traversal_peak measured in this run: trav_step (4 slab tests, sort, push/pop) with converged warps on "
+                                   "64 L1-resident nodes; closest-hit %.1f / any-hit %.1f Gbox-tests/s" % (leg["peak_closest"] / 1e9, leg["peak_any"] / 1e9),
+                    "kernel": "traversal loops: trace_packet_kernel + trace_kernel + shadow_packet_kernel + shadow_kernel",
+                    "launches_per_step": leg["n_trav_launches"], "avg_launch_ms": leg["trav_ms"] / max(1, leg["n_trav_launches"]),
+                    "box_tests_per_launch": leg["my_box_tests"] // max(1, leg["n_trav_launches"]),
+                    "share_of_step": leg["trav_ms"] / leg["serial_ms"], "serialised_step_ms": leg["serial_ms"],
+                    "kernel_class_ms_per_step": leg["class_ms"],
+                    "timing": "CUDA events around every launch, launches serialised on one stream (roofline leg), rank 0's shard",
+                    "box_tests_per_ray": m["box_tests"] / max(m["rays"], 1), "prim_tests_per_ray": m["prim_tests"] / max(m["rays"], 1),
+                    "note": "the scene is L1/L2 resident (DRAM traffic is a few % of the bytes the box tests read), so the bound is "
+                            "instruction issue, not HBM: frac = lanes doing box tests x issue rate relative to a loop with no divergence, "
+                            "no cache misses and no fetch / primitive phases; primitive tests are not counted in `achieved`"}
+
+        def block(m):
+            return {"workload": m["desc"], "name": m["name"], "value": m["value"], "unit": "Mrays/s", "ms_per_step": m["ms_per_step"],
+                    "rays_per_step": m["rays"], "rays": m["ray_classes"], "kernel_ms_per_step": m["kernel_ms_per_step"],
+                    "e2e": m["e2e"], "roofline": roofline(m), "gpu_launches": m["gpu_launches"], "clocks": m["clocks"],
+                    "host": {"scene_load_and_bvh_build_s": m["load_s"]}, **{k: v for k, v in m["render"].items()}}
+
+        R = head["render"]
         line = {
-            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "metric": "Mrays/s", "value": head["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": wl["desc"], "name": args.workload, **R, "parallelism": f"tiles{world}", "tile": list(tile),
-                       "l2": "flushed between steps (256 MiB memset)", "shapes": scene.counts()["shapes"],
-                       "resolution": [width, height]},
-            "rays_per_step": rays, "rays": {"primary": n_primary, "shadow": n_shadow, "secondary": n_secondary},
-            "kernel_ms_per_step": k_ms, "kernel_mrays_per_s": rays / (k_ms * 1e-3) / 1e6,
-            "kernel_class_ms_per_step": {k: float(np.mean(v)) for k, v in class_ms.items()},
-            "gpu_launches": launches_per_step * args.steps,
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(width * height * 3), "ms_per_step": float(np.mean(e2e_s)) * 1e3,
-                    "path": "rt_render (C ABI, pinned host buffers)" if world == 1 else
-                            "rt_scene_upload + rt_render_device + all_gather + D2H"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "wave_loop = trace_kernel + shadow_kernel (two instantiations of one traversal loop)",
-                         "launches_per_step": n_launch, "timed_launches_per_step": trav_launches, "avg_launch_ms": trav / n_launch,
-                         "algorithmic_bytes_per_launch": alg_bytes // world // n_launch,
-                         "share_of_step": trav / float(np.mean(serial_ms)), "serialised_step_ms": float(np.mean(serial_ms)),
-                         "timing": "CUDA events around each launch, launches serialised on one stream (roofline leg)",
-                         "note": "scene is L2/L1 resident: DRAM traffic is a few % of the algorithmic bytes, the loop is issue-bound",
-                         "ncu": ncu_note,
-                         "box_tests_per_ray": node_visits / max(rays, 1), "prim_tests_per_ray": prim_tests / max(rays, 1)},
-            "clocks": clock_info,
-            "host": {"scene_load_and_bvh_build_s": load_s},
+            "config": {"workload": head["desc"], "name": head["name"], **R, "parallelism": f"tiles{world}", "tile": list(tile),
+                       "tile_block": args.tile_block, "l2": "flushed between steps (256 MiB memset)", "shapes": head["shapes"],
+                       "resolution": head["resolution"]},
+            "rays_per_step": head["rays"], "rays": head["ray_classes"],
+            "kernel_ms_per_step": head["kernel_ms_per_step"], "kernel_mrays_per_s": head["rays"] / (head["kernel_ms_per_step"] * 1e-3) / 1e6,
+            "gpu_launches": head["gpu_launches"],
+            "e2e": head["e2e"],
+            "roofline": roofline(head),
+            "clocks": head["clocks"],
+            "host": {"scene_load_and_bvh_build_s": head["load_s"]},
+            "kernel_source_tag": tag,
         }
+        if second is not None:
+            line["secondary"] = block(second)
         if world == 1 and not args.no_cpu_baseline:
             try:
-                res = reference_sample(path, R, repeats=2, target_seconds=3.0)
+                res = reference_sample(head["name"], scene_path_for(head["name"]), R, repeats=2, target_seconds=3.0)
                 cms = float(np.mean(res["seconds"][1:])) * 1e3
-                line["cpu_baseline"] = {
-                    "value": res["rays"] / (cms * 1e-3) / 1e6, "unit": "Mrays/s", "cores": res["cores"], "kind": res["kind"],
-                    "sample": f"{res['rows']} of {res['height']} rows x {res['width']} px x {res['spp']} spp, row bands spread over the frame"}
+                line["cpu_baseline"] = {"value": res["rays"] / (cms * 1e-3) / 1e6, "unit": "Mrays/s", "cores": res["cores"], "kind": res["kind"],
+                                        "sample": sample_text(res)}
             except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU line
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
         print(json.dumps(line))
+    rk.host_barrier()
     if world > 1:
-        dist.destroy_process_group()
+        rk.dist.destroy_process_group()
 
 
 def main():
@@ -419,7 +459,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="mixed100k")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="soup1m")
+    ap.add_argument("--secondary", default="mixed100k", help="second workload reported in the same line ('' = none)")
+    ap.add_argument("--tile-block", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -113,7 +113,14 @@ typedef struct rt_render_params {
                               [1] bit 0: record CUDA events around the trace/shadow/shade/light launches
                                          (rt_scene_last_kernel_times)
                               [2] bit 0: serialise the launches of a frame on the caller's stream (by default the
-                                         shadow/light kernels of a level overlap the next level on a second stream) */
+                                         shadow/light kernels of a level overlap the next level on a second stream)
+                              [3], [4] : render window, x0 | x1 << 16 and y0 | y1 << 16 (both 0 = the whole frame):
+                                         only pixels with x0 <= x < x1, y0 <= y < y1 are rendered -- the frame loop
+                                         of raytracer.cpp:433-476 restricted to a region (band-sampled validation
+                                         against the CPU reference at full benchmark sizes)
+                              [5]      : tile block B (0 or 1 = none): tiles are dealt to the ranks in B x B groups
+                                         instead of singly, so that a rank touches a compact part of the scene per group
+                              [6]      : 0 */
 } rt_render_params;
 
 typedef struct rt_render_stats {
@@ -181,7 +188,10 @@ int rt_scene_dump_wide(const rt_scene* scene, float* out, int32_t max_nodes, int
 
 /* Copies primitives, nodes, materials, lights and textures to the current CUDA device (the
  * "scene resident in HBM" state). Idempotent; rt_render* call it on demand. `bytes` (optional)
- * receives the number of bytes copied host->device. */
+ * receives the number of bytes copied host->device. The copy is asynchronous on the default stream;
+ * every later frame, on whatever stream, waits for it through an event, and a re-upload after
+ * rt_scene_evict waits for the last frame that still reads the old copy. There is ONE frame in flight
+ * per scene and device: frames enqueued on different streams are ordered one behind the other. */
 int rt_scene_upload(rt_scene* scene, uint64_t* bytes);
 /* Marks the device copy stale so that the next upload / render copies the scene host->device
  * again (end-to-end timing). Device and page-locked host allocations are kept until
@@ -192,7 +202,10 @@ int rt_scene_evict(rt_scene* scene);
  * render kernels alone, and everything the call put on the stream. The events are recorded on
  * the launching stream by every call; this getter waits for them, so it can be used after an
  * asynchronous rt_render_device(stats = NULL) without perturbing the timed region. Returns
- * RT_ERR_SCENE if that (asynchronous) frame overflowed a ray queue and therefore dropped rays. */
+ * RT_ERR_SCENE if that (asynchronous) frame overflowed a ray queue and therefore dropped rays.
+ * The overflow of an asynchronous frame is STICKY: the next rt_render_device / rt_render /
+ * rt_scene_last_timing call on the scene that finds the flag halves the batch size and returns
+ * RT_ERR_SCENE once; the caller renders the frame again. */
 int rt_scene_last_timing(rt_scene* scene, float* kernel_ms, float* total_ms);
 
 /* Per-kernel-class CUDA-event times of the most recent frame rendered with reserved[1] bit 0 set:
@@ -214,8 +227,10 @@ int rt_shard_pixels(const rt_scene* scene, const rt_render_params* p, int64_t* n
  * Full-frame buffers; a rank with world > 1 writes only the pixels of its own tiles.
  * Ray queues have a fixed capacity; a scene whose ray trees branch heavily (reflective AND
  * transparent materials) can overflow them, which a synchronous call (stats != NULL) detects and
- * answers by re-rendering with smaller batches, remembered for later calls on this scene. Call once
- * synchronously before a series of asynchronous calls (bench.py's counting pass does). */
+ * answers by re-rendering with smaller batches, remembered for later calls on this scene; an
+ * asynchronous call reports it through the next call (see rt_scene_last_timing). Scenes without a
+ * material that is both reflective and transparent cannot overflow (a level never has more rays than
+ * the batch). */
 int rt_render_device(rt_scene* scene, const rt_render_params* p, uint8_t* rgb8, int32_t* hit_ids, float* linear,
                      void* stream, rt_render_stats* stats);
 
@@ -223,6 +238,29 @@ int rt_render_device(rt_scene* scene, const rt_render_params* p, uint8_t* rgb8, 
  * end-to-end call; total_ms covers all of it. */
 int rt_render(rt_scene* scene, const rt_render_params* p, uint8_t* rgb8, int32_t* hit_ids, float* linear,
               rt_render_stats* stats);
+
+/* The same end-to-end call over SEVERAL GPUs of this process (the north-star's "image sharded across the
+ * GPUs of one box by interleaved screen tiles, scene and BVH replicated, tiles copied to host at frame
+ * end"): replaces the serial frame loop raytracer.cpp:433-476 for the whole frame. One persistent host
+ * thread per device: scene upload (all devices copy from one page-locked staging buffer, in parallel),
+ * render of the device's tiles (p->tile_w x p->tile_h, dealt round-robin, see reserved[5]) into a packed
+ * buffer, ONE device->host copy per output into page-locked memory, scatter into the caller's HOST frame
+ * buffers. No inter-GPU traffic, no NCCL. devices = NULL means ordinals 0..n_devices-1. p->rank / p->world
+ * must be 0 / 1. stats: ray counts summed over the devices, kernel_ms = slowest device, total_ms = host
+ * wall clock of the whole call. The result is bit-identical to rt_render on one device. */
+int rt_render_multi(rt_scene* scene, const rt_render_params* p, int32_t n_devices, const int32_t* devices,
+                    uint8_t* rgb8, int32_t* hit_ids, float* linear, rt_render_stats* stats);
+
+/* Kernels launched for this scene so far (all devices): rt_render* calls add what they enqueue. */
+int rt_scene_launch_count(rt_scene* scene, uint64_t* launches);
+
+/* Measured ceiling of the traversal loop on the current device (the denominator of bench.py's
+ * roofline): the loop's own node step -- four conservative slab tests, sort, push / pop on the
+ * shared-memory stack -- run by fully converged warps over the top n_nodes inner nodes of this scene's
+ * tree (L1-resident), `steps` node visits per thread, best of `repeats` launches. any_hit selects the
+ * occlusion-query flavour (shadow kernels) or the closest-hit one. Returns box tests per second. */
+int rt_traversal_peak(rt_scene* scene, int32_t any_hit, int32_t n_nodes, int32_t steps, int32_t repeats,
+                      double* box_tests_per_s, float* ms);
 
 /* Self-tests of the exactness machinery on the device (tests/test_gpu_properties.py).
  * rt_selftest_boxes: n random (ray, box) pairs -- generic, near-axis-parallel directions, huge

@@ -41,7 +41,7 @@ class _SceneDesc(C.Structure):
 class _Params(C.Structure):
     _fields_ = [("use_bvh", C.c_int32), ("samples_sqrt", C.c_int32), ("light_samples", C.c_int32), ("max_depth", C.c_int32),
                 ("seed", C.c_uint64), ("fixed_time", C.c_float), ("row0", C.c_int32), ("row1", C.c_int32),
-                ("threads", C.c_int32)]
+                ("threads", C.c_int32), ("col0", C.c_int32), ("col1", C.c_int32)]
 
 
 class _NodeDump(C.Structure):
@@ -133,10 +133,12 @@ class OracleScene:
         return [(b.is_leaf, tuple(b.lo), tuple(b.hi), [b.prims[k] for k in range(b.count)]) for b in buf[:n]]
 
     def render(self, use_bvh=False, n_samples_sqrt=4, light_samples=1, max_depth=10, seed=1, fixed_time=-1.0,
-               rows=None, threads=None):
-        """Returns dict(rgb, ids, t, linear, rays=(primary, shadow, secondary))."""
+               rows=None, threads=None, cols=None):
+        """Returns dict(rgb, ids, t, linear, rays=(primary, shadow, secondary)). rows / cols = (first, one past
+        the last): only that window of the frame is rendered (the other pixels of the full-size outputs stay 0 / -1)."""
         p = _Params(int(bool(use_bvh)), int(n_samples_sqrt), int(light_samples), int(max_depth), int(seed), float(fixed_time),
-                    rows[0] if rows else 0, rows[1] if rows else 0, threads or (os.cpu_count() or 1))
+                    rows[0] if rows else 0, rows[1] if rows else 0, threads or (os.cpu_count() or 1),
+                    cols[0] if cols else 0, cols[1] if cols else 0)
         h, w = self.height, self.width
         rgb = np.zeros((h, w, 3), dtype=np.uint8)
         ids = np.full((h, w), -1, dtype=np.int32)
@@ -163,9 +165,16 @@ class RefDriver:
         return json.loads(last[-1]) if last else {}
 
     @classmethod
-    def ids(cls, scene_path, use_bvh=True, time=0.0, tmp="/tmp", cwd=None):
+    def ids(cls, scene_path, use_bvh=True, time=0.0, tmp="/tmp", cwd=None, rows=None, cols=None):
+        """(ids, t, info) of the rows [rows[0], rows[1]) (default: all): arrays of shape (rows, width); with
+        cols only those columns are computed (the others stay 0)."""
         out = os.path.join(tmp, f"ref_ids_{os.getpid()}.bin")
-        info = cls._run(["--scene", scene_path, "--mode", "ids", "--bvh", str(int(use_bvh)), "--time", str(time), "--out-ids", out], cwd)
+        args = ["--scene", scene_path, "--mode", "ids", "--bvh", str(int(use_bvh)), "--time", str(time), "--out-ids", out]
+        if rows:
+            args += ["--rows", str(rows[0]), str(rows[1])]
+        if cols:
+            args += ["--cols", str(cols[0]), str(cols[1])]
+        info = cls._run(args, cwd)
         raw = np.fromfile(out, dtype=np.int32)
         os.remove(out)
         w, h = int(raw[0]), int(raw[1])
@@ -175,12 +184,14 @@ class RefDriver:
 
     @classmethod
     def render(cls, scene_path, use_bvh=True, n_samples_sqrt=1, light_samples=1, max_depth=10, seed=1, rows=None,
-               tmp="/tmp", cwd=None):
+               tmp="/tmp", cwd=None, cols=None):
         out = os.path.join(tmp, f"ref_raw_{os.getpid()}.bin")
         args = ["--scene", scene_path, "--mode", "render", "--bvh", str(int(use_bvh)), "--s", str(n_samples_sqrt),
                 "--light-samples", str(light_samples), "--depth", str(max_depth), "--seed", str(seed), "--out-raw", out]
         if rows:
             args += ["--rows", str(rows[0]), str(rows[1])]
+        if cols:
+            args += ["--cols", str(cols[0]), str(cols[1])]
         info = cls._run(args, cwd)
         raw = np.fromfile(out, dtype=np.uint8)
         os.remove(out)

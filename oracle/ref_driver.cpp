@@ -43,6 +43,7 @@ struct Options {
     int s = 1, light_samples = 1, depth = MAX_RECURSION_DEPTH;
     unsigned seed = 1;
     int row0 = 0, row1 = -1;
+    int col0 = 0, col1 = -1;   // render / ids modes: only columns [col0,col1) of the rows (outputs keep the full width)
     float fixed_time = -1.0f;  // ids mode: ray.time; <0 -> 0
     int repeat = 1;            // render mode: render the band this many times, report each time
 };
@@ -50,7 +51,7 @@ struct Options {
 void usage() {
     std::fprintf(stderr,
         "ref_driver --scene F [--mode render|ids|bvh] [--bvh 0|1] [--s N] [--light-samples N]\n"
-        "           [--depth D] [--seed S] [--rows Y0 Y1] [--time T] [--repeat N]\n"
+        "           [--depth D] [--seed S] [--rows Y0 Y1] [--cols X0 X1] [--time T] [--repeat N]\n"
         "           [--out-ppm F] [--out-raw F] [--out-ids F] [--out-bvh F]\n");
 }
 
@@ -69,6 +70,7 @@ bool parse(int argc, char** argv, Options& o) {
         else if (a == "--depth") o.depth = std::atoi(next("--depth"));
         else if (a == "--seed") o.seed = (unsigned)std::strtoul(next("--seed"), nullptr, 10);
         else if (a == "--rows") { o.row0 = std::atoi(next("--rows")); o.row1 = std::atoi(next("--rows")); }
+        else if (a == "--cols") { o.col0 = std::atoi(next("--cols")); o.col1 = std::atoi(next("--cols")); }
         else if (a == "--time") o.fixed_time = (float)std::atof(next("--time"));
         else if (a == "--repeat") o.repeat = std::max(1, std::atoi(next("--repeat")));
         else if (a == "--out-ppm") o.out_ppm = next("--out-ppm");
@@ -125,6 +127,8 @@ int main(int argc, char** argv) {
 
         const int row0 = std::max(0, opt.row0);
         const int row1 = (opt.row1 < 0 || opt.row1 > height) ? height : opt.row1;
+        const int col0 = std::max(0, opt.col0);
+        const int col1 = (opt.col1 < 0 || opt.col1 > width) ? width : opt.col1;
 
         if (opt.mode == "bvh") {
             FILE* f = opt.out_bvh.empty() ? stdout : std::fopen(opt.out_bvh.c_str(), "w");
@@ -143,7 +147,7 @@ int main(int argc, char** argv) {
             std::vector<float> ts((size_t)width * (row1 - row0));
             auto t0 = std::chrono::steady_clock::now();
             for (int y = row0; y < row1; ++y)
-                for (int x = 0; x < width; ++x) {
+                for (int x = col0; x < col1; ++x) {
                     auto [origin, direction] = camera.pixelToRay_thin_lens({x + 0.5f, y + 0.5f}, gen, dist);
                     Ray ray = {origin, direction};
                     ray.time = opt.fixed_time < 0 ? 0.0f : opt.fixed_time;
@@ -179,7 +183,7 @@ int main(int argc, char** argv) {
         gen.seed(opt.seed);
         auto t0 = std::chrono::steady_clock::now();
         for (int y = row0; y < row1; ++y) {
-            for (int x = 0; x < width; ++x) {
+            for (int x = col0; x < col1; ++x) {
                 Color c = {0.0f, 0.0f, 0.0f};
                 if (opt.s <= 1) {
                     auto [origin, direction] = camera.pixelToRay_thin_lens({x + 0.5f, y + 0.5f}, gen, dist);
@@ -233,8 +237,8 @@ int main(int argc, char** argv) {
         }
         std::string all;
         for (size_t i = 0; i < times.size(); ++i) { char b[32]; std::snprintf(b, sizeof(b), "%s%.6f", i ? "," : "", times[i]); all += b; }
-        std::printf("{\"mode\":\"render\",\"width\":%d,\"rows\":%d,\"spp\":%d,\"seconds\":%.6f,\"all_seconds\":[%s],\"build_seconds\":%.6f}\n",
-                    width, rows, opt.s <= 1 ? 1 : opt.s * opt.s, secs, all.c_str(), build_s);
+        std::printf("{\"mode\":\"render\",\"width\":%d,\"rows\":%d,\"cols\":%d,\"spp\":%d,\"seconds\":%.6f,\"all_seconds\":[%s],\"build_seconds\":%.6f}\n",
+                    width, rows, col1 - col0, opt.s <= 1 ? 1 : opt.s * opt.s, secs, all.c_str(), build_s);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "ref_driver: %s\n", e.what());
         return 1;

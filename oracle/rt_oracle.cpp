@@ -612,13 +612,18 @@ int orc_render(const orc_scene* s, const orc_params* p, uint8_t* rgb8, int32_t* 
     const int W = s->cam.res_x, H = s->cam.res_y;
     if (W <= 0 || H <= 0) return -4;
     const int row0 = std::max(0, p->row0), row1 = (p->row1 <= 0 || p->row1 > H) ? H : p->row1;
+    const int col0 = std::max(0, p->col0), col1 = (p->col1 <= 0 || p->col1 > W) ? W : p->col1;
+    const int wcols = std::max(0, col1 - col0);
+    const long long n_window = (long long)std::max(0, row1 - row0) * wcols;
     const int spp = p->samples_sqrt <= 1 ? 1 : p->samples_sqrt * p->samples_sqrt;
     const int nthreads = std::max(1, p->threads);
     std::vector<uint64_t> counts((size_t)nthreads * 3, 0);
     auto work = [&](int tid) {
         Tracer tr{*s, *p};
-        for (int y = row0 + tid; y < row1; y += nthreads) {
-            for (int x = 0; x < W; x++) {
+        // pixels of the window are dealt to the threads in runs of 8 (a band of a few rows still uses every core)
+        for (long long run = tid; run * 8 < n_window; run += nthreads) {
+            for (long long wi = run * 8; wi < std::min(n_window, run * 8 + 8); wi++) {
+                const int y = row0 + (int)(wi / wcols), x = col0 + (int)(wi % wcols);
                 Draws g = {(uint32_t)(y * W + x), (uint32_t)(p->seed & 0xffffffffu), (uint32_t)(p->seed >> 32), 0u};
                 Rgb sum = {0, 0, 0};
                 int shape0 = -1;

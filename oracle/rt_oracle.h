@@ -52,7 +52,8 @@ typedef struct orc_params {
     uint64_t seed;
     float fixed_time;   /* >= 0: fixed shutter time; < 0: random per sample */
     int32_t row0, row1; /* rows [row0,row1) are rendered; row1 <= 0 means all */
-    int32_t threads;    /* worker threads over rows (results do not depend on it) */
+    int32_t threads;    /* worker threads over the window's pixels (results do not depend on it) */
+    int32_t col0, col1; /* columns [col0,col1) of those rows are rendered; col1 <= 0 means all */
 } orc_params;
 
 typedef struct orc_scene orc_scene;
@@ -65,8 +66,8 @@ int orc_scene_shape_order(const orc_scene* s, int32_t* out, int32_t n);
 typedef struct orc_node_dump { int32_t is_leaf; float lo[3], hi[3]; int32_t count; int32_t prims[4]; } orc_node_dump;
 int orc_scene_dump_bvh(const orc_scene* s, orc_node_dump* out, int32_t max_nodes);
 
-/* Renders rows [row0,row1). Buffers are FULL-frame sized (res_y*res_x); only the rendered rows are
- * written. rays[3] (optional) receives primary / shadow / secondary ray counts. Any output may be NULL. */
+/* Renders rows [row0,row1) x columns [col0,col1). Buffers are FULL-frame sized (res_y*res_x); only the
+ * rendered pixels are written. rays[3] (optional) receives primary / shadow / secondary ray counts. Any output may be NULL. */
 int orc_render(const orc_scene* s, const orc_params* p, uint8_t* rgb8, int32_t* hit_ids, float* hit_t, float* linear,
                uint64_t* rays);
 

@@ -55,6 +55,7 @@ class _Tables:
         self.mat_index = {}
         self.textures = []
         self.tex_index = {}
+        self.by_identity = {}  # id(material dict) -> index: generated scenes share one dict per palette entry
 
     def texture(self, name):
         if len(name) < 3:
@@ -70,6 +71,14 @@ class _Tables:
         return self.tex_index[path]
 
     def material(self, mj):
+        if mj is not None and id(mj) in self.by_identity:
+            return self.by_identity[id(mj)][1]
+        idx = self._material(mj)
+        if mj is not None:
+            self.by_identity[id(mj)] = (mj, idx)  # keeps mj alive, so the id stays unique
+        return idx
+
+    def _material(self, mj):
         # defaults of Material (material.hpp:52-70) when the block is absent
         if mj is None:
             vals = [F(0.8)] * 3 + [F(1.0)] * 3 + [F(0.1), F(0.9), F(0.3), F(20.0), F(0.0), F(0.0), F(0.0), F(1.0)]
@@ -159,7 +168,23 @@ def scene_arrays(scene: dict, texture_dir: str = "../../Textures"):
             shapes.append((2, mat, t, r, sc, list(zero), [F(0)] * 12))
         except (KeyError, ValueError, TypeError):
             continue
-    for pj in scene.get("planes", []):
+    # Bulk path for big generated scenes (millions of well-formed quads): corners converted by numpy in one
+    # go, same narrowing double -> float32. Anything irregular falls through to the per-entry loop below.
+    planes = scene.get("planes", [])
+    plane_block = None
+    if len(planes) > 10000:
+        try:
+            corners = np.asarray([pj["corners"] for pj in planes], dtype=np.float64)
+            if corners.shape == (len(planes), 4, 3) and all(type(c[0][0]) in (float, int) for c in (planes[0]["corners"], planes[-1]["corners"])):
+                plane_block = np.zeros(len(planes), dtype=SHAPE_DTYPE)
+                plane_block["type"] = 3
+                plane_block["material"] = [tabs.material(pj.get("material")) for pj in planes]
+                plane_block["corners"] = corners.reshape(len(planes), 12).astype(np.float32)
+                planes = []
+        except (KeyError, ValueError, TypeError):
+            plane_block = None
+            planes = scene.get("planes", [])
+    for pj in planes:
         if not isinstance(pj, dict) or not isinstance(pj.get("corners"), list) or len(pj["corners"]) != 4:
             continue
         try:
@@ -171,6 +196,8 @@ def scene_arrays(scene: dict, texture_dir: str = "../../Textures"):
     shapes_a = np.zeros(len(shapes), dtype=SHAPE_DTYPE)
     for i, s in enumerate(shapes):
         shapes_a[i] = s
+    if plane_block is not None:
+        shapes_a = np.concatenate([shapes_a, plane_block])
     mats_a = np.zeros(max(1, len(tabs.materials)), dtype=MATERIAL_DTYPE)
     if not tabs.materials:
         tabs.material(None)

@@ -110,6 +110,9 @@ SYMBOLS = {
     "rt_scene_dump_wide": (C.c_int, [_VP, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32)]),
     "rt_scene_last_kernel_times": (C.c_int, [_VP, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "rt_render": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _VP, _VP, C.POINTER(RenderStats)]),
+    "rt_render_multi": (C.c_int, [_VP, C.POINTER(RenderParams), C.c_int32, C.POINTER(C.c_int32), _VP, _VP, _VP, C.POINTER(RenderStats)]),
+    "rt_scene_launch_count": (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
+    "rt_traversal_peak": (C.c_int, [_VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "rt_write_ppm": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, _VP]),
     "rt_read_ppm": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.POINTER(C.c_uint8))]),
     "rt_free": (None, [_VP]),

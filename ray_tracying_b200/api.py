@@ -42,8 +42,11 @@ class Stats:
 def make_params(use_bvh: bool = False, n_samples_sqrt: int = 4, light_samples: int = 1,
                 max_depth: int = MAX_RECURSION_DEPTH, seed: int = 1, fixed_time: float = -1.0, rank: int = 0,
                 world: int = 1, tile: Sequence[int] = (32, 32), collect_stats: bool = False,
-                prune: bool = True, time_kernels: bool = False, serial: bool = False) -> RenderParams:
-    """Defaults are the reference binary's (raytracer.cpp:361-363: BVH off, 4x4 samples, 1 light sample)."""
+                prune: bool = True, time_kernels: bool = False, serial: bool = False,
+                window: Optional[Sequence[int]] = None, tile_block: int = 0) -> RenderParams:
+    """Defaults are the reference binary's (raytracer.cpp:361-363: BVH off, 4x4 samples, 1 light sample).
+    window = (x0, y0, x1, y1): render only that region of the frame; tile_block = B: deal tiles to the
+    ranks in B x B groups."""
     p = RenderParams()
     lib.rt_render_params_default(C.byref(p))
     p.use_bvh = int(bool(use_bvh))
@@ -58,6 +61,13 @@ def make_params(use_bvh: bool = False, n_samples_sqrt: int = 4, light_samples: i
     p.reserved[0] = 0 if prune else 1
     p.reserved[1] = 1 if time_kernels else 0
     p.reserved[2] = 1 if serial else 0
+    if window is not None:
+        x0, y0, x1, y1 = (int(v) for v in window)
+        if not (0 <= x0 < x1 <= 65535 and 0 <= y0 < y1 <= 65535):
+            raise ValueError("window must satisfy 0 <= x0 < x1 <= 65535 and 0 <= y0 < y1 <= 65535")
+        p.reserved[3] = C.c_int32(x0 | (x1 << 16)).value
+        p.reserved[4] = C.c_int32(y0 | (y1 << 16)).value
+    p.reserved[5] = int(tile_block)
     return p
 
 
@@ -217,6 +227,41 @@ class Scene:
         check(lib.rt_render(self._h, C.byref(p), rgb.ctypes.data, ids.ctypes.data if want_ids else None,
                             lin.ctypes.data if want_linear else None, C.byref(st)), "rt_render")
         return rgb, ids, lin, Stats.from_c(st)
+
+    def render_multi(self, params: Optional[RenderParams] = None, n_devices: int = 1, devices: Optional[Sequence[int]] = None,
+                     want_ids: bool = True, want_linear: bool = False, **kw):
+        """rt_render_multi: the whole frame over several GPUs of this process (tiles dealt to the devices, scene
+        replicated, each device's tiles copied to the host at frame end). Same return value as render()."""
+        p = params if params is not None else make_params(**kw)
+        w, h = self.resolution
+        rgb = np.zeros((h, w, 3), dtype=np.uint8)
+        ids = np.full((h, w), -1, dtype=np.int32) if want_ids else None
+        lin = np.zeros((h, w, 3), dtype=np.float32) if want_linear else None
+        dev = (C.c_int32 * n_devices)(*devices) if devices is not None else None
+        st = RenderStats()
+        check(lib.rt_render_multi(self._h, C.byref(p), n_devices, dev, rgb.ctypes.data, ids.ctypes.data if want_ids else None,
+                                  lin.ctypes.data if want_linear else None, C.byref(st)), "rt_render_multi")
+        return rgb, ids, lin, Stats.from_c(st)
+
+    def render_multi_into(self, params: RenderParams, n_devices: int, rgb_ptr: int = 0, ids_ptr: int = 0, linear_ptr: int = 0) -> Stats:
+        """rt_render_multi into caller-owned HOST memory given as raw addresses (page-locked or not)."""
+        st = RenderStats()
+        check(lib.rt_render_multi(self._h, C.byref(params), n_devices, None, rgb_ptr or None, ids_ptr or None, linear_ptr or None,
+                                  C.byref(st)), "rt_render_multi")
+        return Stats.from_c(st)
+
+    def launch_count(self) -> int:
+        """Kernels launched for this scene so far, over all devices (rt_scene_launch_count)."""
+        n = C.c_uint64()
+        check(lib.rt_scene_launch_count(self._h, C.byref(n)), "rt_scene_launch_count")
+        return n.value
+
+    def traversal_peak(self, any_hit: bool = False, n_nodes: int = 64, steps: int = 4096, repeats: int = 5) -> tuple[float, float]:
+        """(box tests per second, ms of the best launch) of the traversal loop's node step with fully converged
+        warps on L1-resident nodes of this scene's tree (rt_traversal_peak): the traversal roofline."""
+        v, ms = C.c_double(), C.c_float()
+        check(lib.rt_traversal_peak(self._h, int(any_hit), n_nodes, steps, repeats, C.byref(v), C.byref(ms)), "rt_traversal_peak")
+        return v.value, ms.value
 
     def render_into(self, params: RenderParams, rgb_ptr: int = 0, ids_ptr: int = 0, linear_ptr: int = 0) -> Stats:
         """Host-buffer render (rt_render) into caller-owned HOST memory given as raw addresses (e.g. a

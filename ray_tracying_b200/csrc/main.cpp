@@ -4,7 +4,8 @@
 // The reference resolves -input under ../../ASCII/ and -output under ../../Output/ relative to
 // its build directory; we do the same unless the argument contains a '/', in which case it is
 // taken as a path. Extra switches (not in the reference): -depth D, -seed S, -textures DIR,
-// -ids FILE (raw int32 primary hit-ID buffer), -stats.
+// -ids FILE (raw int32 primary hit-ID buffer), -stats, -gpus N (shard the frame over N GPUs of this
+// box by screen tiles, rt_render_multi; 0 = all visible GPUs), -tile W H, -tile_block B.
 // Everything is done through the C ABI in include/rt_render.h.
 #include <cstdio>
 #include <cstdlib>
@@ -19,6 +20,7 @@ int main(int argc, char* argv[]) {
     rt_render_params_default(&params);
     std::string scene_name, output_name = "output.ppm", texture_dir, ids_file;
     bool print_stats = false;
+    int gpus = 1;
 
     for (int i = 1; i < argc; ++i) {
         if (std::strcmp(argv[i], "-bvh") == 0) params.use_bvh = 1;
@@ -31,6 +33,9 @@ int main(int argc, char* argv[]) {
         else if (std::strcmp(argv[i], "-textures") == 0 && i + 1 < argc) texture_dir = argv[++i];
         else if (std::strcmp(argv[i], "-ids") == 0 && i + 1 < argc) ids_file = argv[++i];
         else if (std::strcmp(argv[i], "-stats") == 0) print_stats = true;
+        else if (std::strcmp(argv[i], "-gpus") == 0 && i + 1 < argc) gpus = std::atoi(argv[++i]);
+        else if (std::strcmp(argv[i], "-tile") == 0 && i + 2 < argc) { params.tile_w = std::atoi(argv[++i]); params.tile_h = std::atoi(argv[++i]); }
+        else if (std::strcmp(argv[i], "-tile_block") == 0 && i + 1 < argc) params.reserved[5] = std::atoi(argv[++i]);
     }
     if (scene_name.empty()) {
         std::fprintf(stderr, "Error: Please specify scene file name\n");
@@ -62,17 +67,20 @@ int main(int argc, char* argv[]) {
     std::vector<int32_t> ids;
     if (!ids_file.empty()) ids.resize((size_t)width * height);
     rt_render_stats stats;
-    if (rt_render(scene, &params, rgb.data(), ids.empty() ? nullptr : ids.data(), nullptr, &stats) != RT_OK) {
+    if (gpus <= 0) gpus = rt_device_count();
+    const int rc_render = gpus > 1 ? rt_render_multi(scene, &params, gpus, nullptr, rgb.data(), ids.empty() ? nullptr : ids.data(), nullptr, &stats)
+                                   : rt_render(scene, &params, rgb.data(), ids.empty() ? nullptr : ids.data(), nullptr, &stats);
+    if (rc_render != RT_OK) {
         std::fprintf(stderr, "An error occurred: %s\n", rt_last_error());
         rt_scene_destroy(scene);
         return 1;
     }
     std::printf("Rendering complete.\n");
     if (print_stats)
-        std::printf("rays %llu (primary %llu, shadow %llu, secondary %llu), kernel %.3f ms, %.1f Mrays/s\n",
+        std::printf("rays %llu (primary %llu, shadow %llu, secondary %llu), %d GPU%s, kernel %.3f ms, %.1f Mrays/s, end to end %.3f ms\n",
                     (unsigned long long)stats.rays, (unsigned long long)stats.primary_rays,
-                    (unsigned long long)stats.shadow_rays, (unsigned long long)stats.secondary_rays, stats.kernel_ms,
-                    stats.kernel_ms > 0 ? (double)stats.rays / stats.kernel_ms * 1e-3 : 0.0);
+                    (unsigned long long)stats.shadow_rays, (unsigned long long)stats.secondary_rays, gpus, gpus > 1 ? "s" : "",
+                    stats.kernel_ms, stats.kernel_ms > 0 ? (double)stats.rays / stats.kernel_ms * 1e-3 : 0.0, stats.total_ms);
     int rc = 0;
     if (rt_write_ppm(output_file.c_str(), width, height, rgb.data()) != RT_OK) {
         std::fprintf(stderr, "%s\n", rt_last_error());

@@ -26,10 +26,14 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "api_internal.hpp"
@@ -94,9 +98,14 @@ struct FrameParams {
     uint32_t seed_lo, seed_hi;
     float fixed_time;
     int shadow_per_rec;  // shadow rays per shaded hit = sum over lights of (radius > 0 ? light_samples : 1)
-    // screen tiles of this rank
+    // screen tiles of this rank (TilePlan): tiles[i] = index of the i-th tile this rank renders,
+    // tile_slot[t] = i for those tiles and -1 for every other tile of the frame
     int tile_w, tile_h, tiles_x, n_tiles, rank, world, n_my_tiles;
     int sub_x, sub_per_tile;  // 8x4 pixel blocks per tile
+    const int* __restrict__ tiles;
+    const int* __restrict__ tile_slot;
+    int win_x0, win_y0, win_x1, win_y1;  // only pixels inside this window are rendered (whole frame by default)
+    int packed;  // 1: outputs are indexed tile-major over this rank's tiles (rt_render_multi) instead of frame row-major
     // wavefront buffers
     float4* q[2];                  // ray queues (ping-pong by level parity), 3 x float4 per ray
     int* hit_prim;                 // closest primitive per ray of the current level (-1 = miss)
@@ -107,8 +116,20 @@ struct FrameParams {
     int* hit_ids;                  // optional frame-sized output
     unsigned int* lvl;             // [RT_MAX_DEPTH + 2][RT_LVL_STRIDE] per-level counters
     unsigned long long* totals;    // [8] frame totals
+    unsigned int* overflow_host;   // page-locked host word (mapped): set when a ray queue overflowed
     int capacity;                  // rays per queue
 };
+
+// Is pixel (x, y) rendered by this rank / inside the window, and where does its output go?
+// Returns -1 for a pixel this rank does not render.
+RT_DEV long long out_index(const FrameParams& p, int x, int y) {
+    if (x < p.win_x0 || x >= p.win_x1 || y < p.win_y0 || y >= p.win_y1) return -1;
+    const int tx = x / p.tile_w, ty = y / p.tile_h;
+    const int slot = __ldg(p.tile_slot + ty * p.tiles_x + tx);
+    if (slot < 0) return -1;
+    if (!p.packed) return (long long)y * p.res_x + x;
+    return ((long long)slot * p.tile_h + (y - ty * p.tile_h)) * p.tile_w + (x - tx * p.tile_w);
+}
 
 // Ray record: a = (origin, time)  b = (direction, weight)  c = bits(pixel, sample, node, 0)
 // Shade record: r0 = (P, bits pixel) r1 = (N, weight * local share) r2 = (V, bits material)
@@ -172,10 +193,10 @@ __global__ void __launch_bounds__(256) gen_kernel(const __grid_constant__ FrameP
         const int s = (int)(unit % p.spp);
         const long long blk = unit / p.spp;
         const int sub = (int)(blk % p.sub_per_tile);
-        const int tile = (int)(blk / p.sub_per_tile) * p.world + p.rank;
+        const int tile = __ldg(p.tiles + (int)(blk / p.sub_per_tile));
         const int lx = (sub % p.sub_x) * 8 + (lane & 7), ly = (sub / p.sub_x) * 4 + (lane >> 3);
         const int x = (tile % p.tiles_x) * p.tile_w + lx, y = (tile / p.tiles_x) * p.tile_h + ly;
-        const bool valid = lx < p.tile_w && ly < p.tile_h && x < p.res_x && y < p.res_y;
+        const bool valid = lx < p.tile_w && ly < p.tile_h && x < p.win_x1 && y < p.win_y1 && x >= p.win_x0 && y >= p.win_y0;
         const unsigned int slot = (unsigned int)w * 32u + (unsigned int)lane;  // one packet per unit, no compaction
         {
             const unsigned int live = __ballot_sync(0xffffffffu, valid);
@@ -525,7 +546,7 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
         if (live && !dead && prim < 0) {
             const float bg = weight * 0.1f;  // background {0.1,0.1,0.1} (raytracer.cpp:297)
             accumulate(p, pixel, bg, bg, bg);
-            if (node == 1u && sample == 0u && p.hit_ids) p.hit_ids[pixel] = -1;
+            if (node == 1u && sample == 0u && p.hit_ids) p.hit_ids[out_index(p, (int)(pixel % (uint32_t)p.res_x), (int)(pixel / (uint32_t)p.res_x))] = -1;
         }
         const bool hit = live && !dead && prim >= 0;
         Ray r;
@@ -542,7 +563,8 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
             m2 = __ldg(p.mats + 4 * mat + 2);
             m3 = __ldg(p.mats + 4 * mat + 3);
             if (node == 1u && sample == 0u && p.hit_ids)
-                p.hit_ids[pixel] = __float_as_int(__ldg(p.bvh.prims + (size_t)prim * 8 + 7).x);
+                p.hit_ids[out_index(p, (int)(pixel % (uint32_t)p.res_x), (int)(pixel / (uint32_t)p.res_x))] =
+                    __float_as_int(__ldg(p.bvh.prims + (size_t)prim * 8 + 7).x);
         }
         const float roughness = m2.z, reflectivity = m2.w, transparency = m3.x, ior = m3.y;
 
@@ -649,6 +671,7 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
                 o[2] = make_float4(c.x, c.y, __uint_as_float(node * 2u), 0.0f);
             } else {
                 p.totals[T_OVERFLOW] = 1ull;
+                *p.overflow_host = 1u;
             }
         }
         if (want_refr) {
@@ -659,6 +682,7 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
                 o[2] = make_float4(c.x, c.y, __uint_as_float(node * 2u + 1u), 0.0f);
             } else {
                 p.totals[T_OVERFLOW] = 1ull;
+                *p.overflow_host = 1u;
             }
         }
     }
@@ -961,9 +985,7 @@ __global__ void clear_accum_kernel(const __grid_constant__ FrameParams p) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = p.res_x * p.res_y;
     if (idx >= n) return;
-    const int x = idx % p.res_x, y = idx / p.res_x;
-    const int tile = (y / p.tile_h) * p.tiles_x + (x / p.tile_w);
-    if (tile % p.world != p.rank) return;
+    if (out_index(p, idx % p.res_x, idx / p.res_x) < 0) return;
     p.accum[(size_t)idx * 3 + 0] = 0ull; p.accum[(size_t)idx * 3 + 1] = 0ull; p.accum[(size_t)idx * 3 + 2] = 0ull;
 }
 
@@ -972,9 +994,8 @@ __global__ void finalize_kernel(const __grid_constant__ FrameParams p, uint8_t* 
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = p.res_x * p.res_y;
     if (idx >= n) return;
-    const int x = idx % p.res_x, y = idx / p.res_x;
-    const int tile = (y / p.tile_h) * p.tiles_x + (x / p.tile_w);
-    if (tile % p.world != p.rank) return;
+    const long long o = out_index(p, idx % p.res_x, idx / p.res_x);
+    if (o < 0) return;
     const double inv = 1.0 / 1099511627776.0;
     float c[3];
 #pragma unroll
@@ -982,7 +1003,7 @@ __global__ void finalize_kernel(const __grid_constant__ FrameParams p, uint8_t* 
         c[k] = (float)((double)(long long)p.accum[(size_t)idx * 3 + k] * inv);
         if (p.samples_sqrt > 1) c[k] = c[k] / (float)p.spp;
     }
-    if (linear) { linear[3 * (size_t)idx + 0] = c[0]; linear[3 * (size_t)idx + 1] = c[1]; linear[3 * (size_t)idx + 2] = c[2]; }
+    if (linear) { linear[3 * (size_t)o + 0] = c[0]; linear[3 * (size_t)o + 1] = c[1]; linear[3 * (size_t)o + 2] = c[2]; }
     if (rgb8) {
         const float inv_gamma = 1.0f / 1.1f;
 #pragma unroll
@@ -992,23 +1013,33 @@ __global__ void finalize_kernel(const __grid_constant__ FrameParams p, uint8_t* 
             v = (0.0f < v) ? v : 0.0f;
             int q = (int)((double)v * 255.999);
             q = max(0, min(q, 255));
-            rgb8[3 * (size_t)idx + k] = (uint8_t)q;
+            rgb8[3 * (size_t)o + k] = (uint8_t)q;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Host side: device scene, buffers, launches
+// Host side: device scenes (one per CUDA device), buffers, launches
 // ---------------------------------------------------------------------------------------------
+
+// Which screen tiles a rank renders, as device arrays (gen_kernel / out_index read them). Cached per
+// (frame geometry, tile size, rank, world, block, window) in the DeviceScene.
+struct TilePlan {
+    int key[12] = {0};
+    std::vector<int> tiles;  // this rank's tiles, increasing
+    int* d_tiles = nullptr;
+    int* d_slot = nullptr;
+    int64_t pixels = 0;      // pixels this rank renders (inside the window)
+};
+
 struct DeviceScene {
     int device = -1;
-    // The scene lives in ONE device arena filled from ONE page-locked host staging buffer, so
-    // making the scene resident is a single asynchronous H2D copy. Both are allocated once per
-    // scene; rt_scene_evict only marks the device copy stale.
+    // The scene lives in ONE device arena filled from ONE page-locked host staging buffer (shared by
+    // all devices, DeviceSet::staging), so making the scene resident is a single asynchronous H2D
+    // copy. Allocated once per scene and device; rt_scene_evict only marks the device copy stale.
     uint8_t* arena = nullptr;
-    uint8_t* staging = nullptr;  // cudaMallocHost
-    size_t arena_bytes = 0;
     bool resident = false;
+    cudaEvent_t ev_upload = nullptr;  // recorded behind the arena copy: every frame waits for it
     float4* prims = nullptr;
     float* wide = nullptr;
     float4* leafbox = nullptr;
@@ -1016,13 +1047,13 @@ struct DeviceScene {
     float4* lights = nullptr;
     DTexture* textures = nullptr;
     uint8_t* texels = nullptr;
-    uint64_t bytes = 0;  // payload bytes (what an upload copies)
     // wavefront buffers
     float4* q[2] = {nullptr, nullptr};
     int* hit_prim = nullptr;
     float4* recs[2] = {nullptr, nullptr};
     int* vis[2] = {nullptr, nullptr};
     cudaStream_t aux = nullptr;                  // shadow + light kernels run here, overlapping the next level
+    cudaStream_t own = nullptr;                  // rt_render_multi: this device's frame stream
     std::vector<cudaEvent_t> ev_shade, ev_light;  // per level
     long long capacity = 0;
     int vis_lights = 0;
@@ -1030,6 +1061,8 @@ struct DeviceScene {
     size_t accum_pixels = 0;
     unsigned int* lvl = nullptr;
     unsigned long long* totals = nullptr;
+    unsigned int* overflow_host = nullptr;  // page-locked, mapped: set by shade_kernel when a queue overflows
+    bool async_pending = false;             // the last frame was asynchronous: its overflow flag has not been looked at
     // (pixel, sample) pairs per batch; halved on queue overflow. Large batches keep the waves of the
     // deeper recursion levels big (a level of a batch is one launch); RT_B200_BATCH_SLOTS overrides.
     long long batch_slots = [] { const char* e = std::getenv("RT_B200_BATCH_SLOTS"); return e ? std::atoll(e) : (8ll << 20); }();
@@ -1040,50 +1073,97 @@ struct DeviceScene {
     size_t stack_bytes = 0;
     bool timed = false;
     int last_launches = 0;
+    unsigned long long total_launches = 0;  // kernels launched on this device for this scene, ever
     // optional per-kernel-class timing (rt_render_params.reserved[1] & 1): event pairs around the
     // trace / shadow / shade / light launches of the most recent frame
     std::vector<cudaEvent_t> class_ev;
     std::vector<int> class_of;  // class of pair i: 0 trace, 1 shadow, 2 shade, 3 light
     int class_launches[4] = {0, 0, 0, 0};  // all launches of the frame per class (timed or not)
-    // frame-sized device outputs of rt_render (host-buffer entry point), kept between calls
+    std::vector<TilePlan*> plans;
+    // device outputs of rt_render / rt_render_multi, kept between calls
     uint8_t* out_rgb = nullptr;
     int32_t* out_ids = nullptr;
     float* out_lin = nullptr;
     size_t out_pixels = 0;
+    // rt_render_multi: page-locked host landing zone of this device's packed tiles
+    uint8_t* host_rgb = nullptr;
+    int32_t* host_ids = nullptr;
+    float* host_lin = nullptr;
+    size_t host_pixels = 0;
+};
+
+struct MultiGpu;
+
+// Everything a scene owns on the CUDA side (HostScene::dev).
+struct DeviceSet {
+    std::mutex mu;
+    std::vector<DeviceScene*> devs;  // by CUDA device ordinal
+    uint8_t* staging = nullptr;      // cudaHostAlloc(portable): the packed scene, source of every upload
+    size_t arena_bytes = 0;
+    size_t o_prims = 0, o_wide = 0, o_leafbox = 0, o_mats = 0, o_lights = 0, o_tex = 0, o_texels = 0;
+    uint64_t bytes = 0;  // payload bytes (what an upload copies)
+    MultiGpu* multi = nullptr;
 };
 
 #define CUDA_TRY(expr)                                                                         \
     do {                                                                                       \
         cudaError_t _e = (expr);                                                               \
         if (_e != cudaSuccess) {                                                               \
-            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                     \
+            rtb::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                \
             return RT_ERR_CUDA;                                                                \
         }                                                                                      \
     } while (0)
 
+static void free_plan(TilePlan* t) {
+    if (!t) return;
+    cudaFree(t->d_tiles);
+    cudaFree(t->d_slot);
+    delete t;
+}
+
 static void free_device(DeviceScene* d) {
     if (!d) return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (d->device >= 0) cudaSetDevice(d->device);
     cudaFree(d->arena);
-    if (d->staging) cudaFreeHost(d->staging);
     cudaFree(d->q[0]); cudaFree(d->q[1]); cudaFree(d->hit_prim);
     for (int i = 0; i < 2; ++i) { cudaFree(d->recs[i]); cudaFree(d->vis[i]); }
     if (d->aux) cudaStreamDestroy(d->aux);
+    if (d->own) cudaStreamDestroy(d->own);
     for (cudaEvent_t e : d->ev_shade) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : d->ev_light) if (e) cudaEventDestroy(e);
     cudaFree(d->accum); cudaFree(d->lvl); cudaFree(d->totals);
+    if (d->overflow_host) cudaFreeHost(d->overflow_host);
     cudaFree(d->out_rgb); cudaFree(d->out_ids); cudaFree(d->out_lin);
+    if (d->host_rgb) cudaFreeHost(d->host_rgb);
+    if (d->host_ids) cudaFreeHost(d->host_ids);
+    if (d->host_lin) cudaFreeHost(d->host_lin);
     for (cudaEvent_t e : d->ev) if (e) cudaEventDestroy(e);
+    if (d->ev_upload) cudaEventDestroy(d->ev_upload);
     for (cudaEvent_t e : d->class_ev) if (e) cudaEventDestroy(e);
+    for (TilePlan* t : d->plans) free_plan(t);
     delete d;
+    cudaSetDevice(cur);
+    cudaGetLastError();
 }
 
+static void multi_shutdown(MultiGpu* m);
+
 void device_release(HostScene& h) {
-    free_device(h.dev);
+    DeviceSet* set = h.dev;
+    if (!set) return;
+    multi_shutdown(set->multi);
+    for (DeviceScene* d : set->devs) free_device(d);
+    if (set->staging) cudaFreeHost(set->staging);
+    cudaGetLastError();
+    delete set;
     h.dev = nullptr;
 }
 
 void device_invalidate(HostScene& h) {
-    if (h.dev) h.dev->resident = false;
+    if (!h.dev) return;
+    for (DeviceScene* d : h.dev->devs) if (d) d->resident = false;
 }
 
 template <typename T>
@@ -1098,31 +1178,55 @@ static void stage(uint8_t* staging, size_t at, const std::vector<T>& v, uint64_t
     bytes += v.size() * sizeof(T);
 }
 
-// First call for a scene: allocations, packing of the host arrays into the staging buffer,
-// occupancy queries. Every call: one H2D copy of the arena on `stream` (if not resident).
-static int make_resident(HostScene& h, cudaStream_t stream, uint64_t* bytes_out) {
-    if (bytes_out) *bytes_out = 0;
-    if (!h.dev) {
-        DeviceScene* d = new DeviceScene();
-        h.dev = d;
-        CUDA_TRY(cudaGetDevice(&d->device));
-        size_t off = 0;
-        const size_t o_prims = place(h.dprims, off), o_wide = place(h.dwide, off), o_leafbox = place(h.dleafbox, off), o_mats = place(h.dmaterials, off);
-        const size_t o_lights = place(h.dlights, off), o_tex = place(h.dtextures, off), o_texels = place(h.texels, off);
-        d->arena_bytes = off;
-        CUDA_TRY(cudaMalloc((void**)&d->arena, d->arena_bytes));
-        CUDA_TRY(cudaMallocHost((void**)&d->staging, d->arena_bytes));
-        std::memset(d->staging, 0, d->arena_bytes);
-        stage(d->staging, o_prims, h.dprims, d->bytes); stage(d->staging, o_wide, h.dwide, d->bytes);
-        stage(d->staging, o_leafbox, h.dleafbox, d->bytes);
-        stage(d->staging, o_mats, h.dmaterials, d->bytes); stage(d->staging, o_lights, h.dlights, d->bytes);
-        stage(d->staging, o_tex, h.dtextures, d->bytes); stage(d->staging, o_texels, h.texels, d->bytes);
-        d->prims = (float4*)(d->arena + o_prims); d->wide = (float*)(d->arena + o_wide); d->leafbox = (float4*)(d->arena + o_leafbox);
-        d->mats = (float4*)(d->arena + o_mats); d->lights = (float4*)(d->arena + o_lights);
-        d->textures = (DTexture*)(d->arena + o_tex); d->texels = d->arena + o_texels;
+// The scene packed into page-locked host memory, once per scene (whatever the number of devices).
+static int ensure_staging(HostScene& h) {
+    if (!h.dev) h.dev = new DeviceSet();
+    DeviceSet* set = h.dev;
+    std::lock_guard<std::mutex> lock(set->mu);
+    if (set->staging) return RT_OK;
+    size_t off = 0;
+    set->o_prims = place(h.dprims, off); set->o_wide = place(h.dwide, off); set->o_leafbox = place(h.dleafbox, off);
+    set->o_mats = place(h.dmaterials, off); set->o_lights = place(h.dlights, off); set->o_tex = place(h.dtextures, off);
+    set->o_texels = place(h.texels, off);
+    set->arena_bytes = off;
+    uint8_t* st = nullptr;
+    CUDA_TRY(cudaHostAlloc((void**)&st, set->arena_bytes, cudaHostAllocPortable));
+    std::memset(st, 0, set->arena_bytes);
+    set->bytes = 0;
+    stage(st, set->o_prims, h.dprims, set->bytes); stage(st, set->o_wide, h.dwide, set->bytes);
+    stage(st, set->o_leafbox, h.dleafbox, set->bytes);
+    stage(st, set->o_mats, h.dmaterials, set->bytes); stage(st, set->o_lights, h.dlights, set->bytes);
+    stage(st, set->o_tex, h.dtextures, set->bytes); stage(st, set->o_texels, h.texels, set->bytes);
+    set->staging = st;
+    return RT_OK;
+}
+
+// The DeviceScene of the CURRENT CUDA device (created on first use).
+static int device_scene(HostScene& h, DeviceScene** out) {
+    int rc = ensure_staging(h);
+    if (rc != RT_OK) return rc;
+    DeviceSet* set = h.dev;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lock(set->mu);
+        if ((int)set->devs.size() <= dev) set->devs.resize((size_t)dev + 1, nullptr);
+        if (set->devs[dev]) { *out = set->devs[dev]; return RT_OK; }
+    }
+    DeviceScene* d = new DeviceScene();
+    d->device = dev;
+    auto init = [&]() -> int {
+        CUDA_TRY(cudaMalloc((void**)&d->arena, set->arena_bytes));
+        d->prims = (float4*)(d->arena + set->o_prims); d->wide = (float*)(d->arena + set->o_wide);
+        d->leafbox = (float4*)(d->arena + set->o_leafbox);
+        d->mats = (float4*)(d->arena + set->o_mats); d->lights = (float4*)(d->arena + set->o_lights);
+        d->textures = (DTexture*)(d->arena + set->o_tex); d->texels = d->arena + set->o_texels;
         CUDA_TRY(cudaMalloc((void**)&d->lvl, (RT_MAX_DEPTH + 2) * RT_LVL_STRIDE * sizeof(unsigned int)));
         CUDA_TRY(cudaMalloc((void**)&d->totals, 8 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaHostAlloc((void**)&d->overflow_host, 64, cudaHostAllocMapped));
+        *d->overflow_host = 0u;
         for (auto& e : d->ev) CUDA_TRY(cudaEventCreate(&e));
+        CUDA_TRY(cudaEventCreateWithFlags(&d->ev_upload, cudaEventDisableTiming));
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
         d->sm_count = prop.multiProcessorCount;
@@ -1140,36 +1244,58 @@ static int make_resident(HostScene& h, cudaStream_t stream, uint64_t* bytes_out)
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->shadow_blocks, shadow_kernel<false>, RT_TRACE_THREADS, d->stack_bytes));
         d->trace_blocks = std::max(1, d->trace_blocks);
         d->shadow_blocks = std::max(1, d->shadow_blocks);
-    }
-    DeviceScene* d = h.dev;
-    if (!d->resident) {
-        CUDA_TRY(cudaMemcpyAsync(d->arena, d->staging, d->arena_bytes, cudaMemcpyHostToDevice, stream));
-        d->resident = true;
-        if (bytes_out) *bytes_out = d->bytes;
-    }
+        return RT_OK;
+    };
+    rc = init();
+    if (rc != RT_OK) { free_device(d); return rc; }  // never keep a half-initialised device scene
+    std::lock_guard<std::mutex> lock(set->mu);
+    set->devs[dev] = d;
+    *out = d;
     return RT_OK;
 }
 
-static int ensure_uploaded(HostScene& h, cudaStream_t stream, uint64_t* bytes_out) {
+// Makes the scene resident on the current device: one H2D copy of the arena on `stream`, ordered
+// BEHIND the last frame that still reads the old copy and AHEAD of every later frame (ev_upload),
+// whatever streams those frames use.
+static int ensure_uploaded(HostScene& h, cudaStream_t stream, uint64_t* bytes_out, DeviceScene** out = nullptr) {
+    if (bytes_out) *bytes_out = 0;
     int count = 0;
-    if (!h.dev && (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)) {
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
         cudaGetLastError();
         set_error("no CUDA device: the renderer has no CPU fallback");
         return RT_ERR_CUDA;
     }
-    const bool fresh = h.dev == nullptr;
-    const int rc = make_resident(h, stream, bytes_out);
-    if (rc != RT_OK && fresh) device_release(h);  // never keep a half-initialised device scene
-    return rc;
+    DeviceScene* d = nullptr;
+    const int rc = device_scene(h, &d);
+    if (rc != RT_OK) return rc;
+    if (!d->resident) {
+        if (d->timed) CUDA_TRY(cudaStreamWaitEvent(stream, d->ev[2], 0));
+        CUDA_TRY(cudaMemcpyAsync(d->arena, h.dev->staging, h.dev->arena_bytes, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaEventRecord(d->ev_upload, stream));
+        d->resident = true;
+        if (bytes_out) *bytes_out = h.dev->bytes;
+    }
+    if (out) *out = d;
+    return RT_OK;
+}
+
+// rank that renders tile (tx, ty): tiles are dealt round-robin, singly (block <= 1) or in
+// block x block groups (a rank then touches a compact part of the scene per group)
+static inline int tile_owner(int tx, int ty, int tiles_x, int world, int block) {
+    if (block <= 1) return (ty * tiles_x + tx) % world;
+    const int bx = (tiles_x + block - 1) / block;
+    return ((ty / block) * bx + tx / block) % world;
 }
 
 static int fill_params(const HostScene& h, const rt_render_params& rp, FrameParams& k) {
     if (h.cam.res_x <= 0 || h.cam.res_y <= 0) { set_error("Camera resolution is 0. Check scene.json."); return RT_ERR_SCENE; }
+    if (h.cam.res_x > 65535 || h.cam.res_y > 65535) { set_error("resolution above 65535 is not supported"); return RT_ERR_SCENE; }
     if (rp.world < 1 || rp.rank < 0 || rp.rank >= rp.world) { set_error("rank/world out of range"); return RT_ERR_INVALID; }
     if (rp.tile_w < 8 || rp.tile_h < 4 || rp.tile_w % 8 || rp.tile_h % 4) { set_error("tile_w must be a multiple of 8 and tile_h of 4"); return RT_ERR_INVALID; }
     if (rp.max_depth < 0 || rp.max_depth > RT_MAX_DEPTH) { set_error("max_depth must be in [0,16]"); return RT_ERR_INVALID; }
     if (rp.light_samples < 1 || rp.light_samples > 65535) { set_error("light_samples must be in [1,65535]"); return RT_ERR_INVALID; }
     if (rp.samples_sqrt > 1024) { set_error("samples_sqrt must be <= 1024"); return RT_ERR_INVALID; }
+    if (rp.reserved[5] < 0 || rp.reserved[5] > 1024) { set_error("tile block must be in [0,1024]"); return RT_ERR_INVALID; }
     std::memset(&k, 0, sizeof(k));
     k.bvh.n_prims = (int)h.dprims.size();
     k.bvh.use_bvh = rp.use_bvh ? 1 : 0;
@@ -1201,36 +1327,91 @@ static int fill_params(const HostScene& h, const rt_render_params& rp, FramePara
     k.n_tiles = k.tiles_x * tiles_y;
     k.rank = rp.rank;
     k.world = rp.world;
-    k.n_my_tiles = (k.n_tiles - rp.rank + rp.world - 1) / rp.world;
     k.sub_x = k.tile_w / 8;
     k.sub_per_tile = k.sub_x * (k.tile_h / 4);
+    // reserved[3] / [4]: render window x0 | x1 << 16, y0 | y1 << 16 (0 = whole frame)
+    k.win_x0 = 0; k.win_y0 = 0; k.win_x1 = k.res_x; k.win_y1 = k.res_y;
+    if (rp.reserved[3] != 0 || rp.reserved[4] != 0) {
+        const uint32_t wx = (uint32_t)rp.reserved[3], wy = (uint32_t)rp.reserved[4];
+        k.win_x0 = (int)(wx & 0xffffu); k.win_x1 = std::min(k.res_x, (int)(wx >> 16));
+        k.win_y0 = (int)(wy & 0xffffu); k.win_y1 = std::min(k.res_y, (int)(wy >> 16));
+        if (k.win_x0 >= k.win_x1 || k.win_y0 >= k.win_y1) { set_error("empty render window"); return RT_ERR_INVALID; }
+    }
     return RT_OK;
 }
 
-static int64_t shard_pixels(const FrameParams& k) {
-    int64_t n = 0;
-    for (int t = k.rank; t < k.n_tiles; t += k.world) {
+// The tiles of (rank, world, block) that intersect the window, in increasing order.
+static void plan_tiles(const FrameParams& k, int block, std::vector<int>& tiles, int64_t& pixels) {
+    tiles.clear();
+    pixels = 0;
+    for (int t = 0; t < k.n_tiles; ++t) {
         const int tx = t % k.tiles_x, ty = t / k.tiles_x;
-        const int w = std::min(k.tile_w, k.res_x - tx * k.tile_w);
-        const int hh = std::min(k.tile_h, k.res_y - ty * k.tile_h);
-        n += (int64_t)w * hh;
+        if (tile_owner(tx, ty, k.tiles_x, k.world, block) != k.rank) continue;
+        const int x0 = std::max(tx * k.tile_w, k.win_x0), x1 = std::min((tx + 1) * k.tile_w, k.win_x1);
+        const int y0 = std::max(ty * k.tile_h, k.win_y0), y1 = std::min((ty + 1) * k.tile_h, k.win_y1);
+        if (x0 >= x1 || y0 >= y1) continue;
+        tiles.push_back(t);
+        pixels += (int64_t)(x1 - x0) * (y1 - y0);
     }
-    return n;
 }
 
-// Queue capacity is decoupled from the batch size: ray trees with reflective AND transparent
-// materials can double per level, so the queues get room for 16x the batch (at most 6M rays,
-// at least 2x the batch); if a level still overflows, the frame is re-rendered with half the batch.
-static long long wanted_capacity(long long batch_slots) {
+static int ensure_plan(DeviceScene* d, FrameParams& k, int block, cudaStream_t stream, TilePlan** out) {
+    const int key[12] = {k.res_x, k.res_y, k.tile_w, k.tile_h, k.rank, k.world, block, k.win_x0, k.win_y0, k.win_x1, k.win_y1, 0};
+    TilePlan* plan = nullptr;
+    for (TilePlan* t : d->plans) if (std::memcmp(t->key, key, sizeof(key)) == 0) { plan = t; break; }
+    if (!plan) {
+        if (d->plans.size() >= 64) {  // frames still in flight may read the old plans: drain before dropping them
+            CUDA_TRY(cudaDeviceSynchronize());
+            for (TilePlan* t : d->plans) free_plan(t);
+            d->plans.clear();
+        }
+        plan = new TilePlan();
+        std::memcpy(plan->key, key, sizeof(key));
+        plan_tiles(k, block, plan->tiles, plan->pixels);
+        std::vector<int> slot((size_t)k.n_tiles, -1);
+        for (size_t i = 0; i < plan->tiles.size(); ++i) slot[plan->tiles[i]] = (int)i;
+        cudaError_t e = cudaMalloc((void**)&plan->d_tiles, std::max<size_t>(1, plan->tiles.size()) * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&plan->d_slot, (size_t)k.n_tiles * sizeof(int));
+        // pageable sources: the copies are staged before the calls return, so `slot` may go out of scope
+        if (e == cudaSuccess && !plan->tiles.empty())
+            e = cudaMemcpyAsync(plan->d_tiles, plan->tiles.data(), plan->tiles.size() * sizeof(int), cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(plan->d_slot, slot.data(), slot.size() * sizeof(int), cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) { free_plan(plan); set_error(std::string("tile plan: ") + cudaGetErrorString(e)); return RT_ERR_CUDA; }
+        d->plans.push_back(plan);
+    }
+    k.tiles = plan->d_tiles;
+    k.tile_slot = plan->d_slot;
+    k.n_my_tiles = (int)plan->tiles.size();
+    *out = plan;
+    return RT_OK;
+}
+
+// Rays of a level per (pixel, sample) of the batch: a hit spawns at most one reflection and one
+// refraction ray, so a scene without a material that is reflective AND transparent never has more
+// rays at any level than at level 0.
+static int ray_tree_branching(const HostScene& h) {
+    int b = 0;
+    for (const rt_material_desc& m : h.materials) b = std::max(b, (m.reflectivity > 0.0f ? 1 : 0) + (m.transparency > 0.0f ? 1 : 0));
+    return b;
+}
+
+// Queue capacity (rays per level of a batch). Branching <= 1: the batch itself bounds every level.
+// Branching 2 (reflective AND transparent materials): ray trees can double per level, so the queues
+// get room for 16x the batch, but at most 6M rays unless the batch itself is larger -- then 2x the
+// batch; if a level still overflows, the frame is re-rendered with half the batch.
+static long long wanted_capacity(long long batch_slots, int branching) {
+    if (branching <= 1) return std::max<long long>(batch_slots, 65536);
     return std::max<long long>(std::max<long long>(2 * batch_slots, 65536), std::min<long long>(16 * batch_slots, 6ll << 20));
 }
 
-static int ensure_buffers(DeviceScene* d, const FrameParams& k, long long batch_slots) {
-    const long long want_cap = wanted_capacity(batch_slots);
+static int ensure_buffers(DeviceScene* d, const FrameParams& k, long long batch_slots, int branching) {
+    const long long want_cap = wanted_capacity(batch_slots, branching);
     if (want_cap > (1ll << 30)) { set_error("batch too large"); return RT_ERR_INVALID; }
     if (want_cap > d->capacity || k.n_lights > d->vis_lights) {
         const long long cap = std::max(want_cap, d->capacity);
         const int nl = std::max(1, std::max(k.n_lights, d->vis_lights));
+        CUDA_TRY(cudaDeviceSynchronize());  // frames in flight on other streams still use the old buffers
         cudaFree(d->q[0]); cudaFree(d->q[1]); cudaFree(d->hit_prim);
         d->q[0] = d->q[1] = nullptr; d->hit_prim = nullptr;
         for (int i = 0; i < 2; ++i) { cudaFree(d->recs[i]); cudaFree(d->vis[i]); d->recs[i] = nullptr; d->vis[i] = nullptr; }
@@ -1247,6 +1428,7 @@ static int ensure_buffers(DeviceScene* d, const FrameParams& k, long long batch_
     }
     const size_t pixels = (size_t)k.res_x * k.res_y;
     if (pixels > d->accum_pixels) {
+        CUDA_TRY(cudaDeviceSynchronize());
         cudaFree(d->accum);
         d->accum = nullptr;
         d->accum_pixels = 0;
@@ -1257,21 +1439,31 @@ static int ensure_buffers(DeviceScene* d, const FrameParams& k, long long batch_
 }
 
 // Enqueues one frame on `stream` (no host synchronisation).
-static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time_classes, bool serial, uint8_t* rgb8, float* linear,
-                         cudaStream_t stream) {
+static int enqueue_frame(const HostScene& h, DeviceScene* d, FrameParams& k, bool collect, bool time_classes, bool serial, uint8_t* rgb8,
+                         float* linear, cudaStream_t stream) {
     const long long total_units = (long long)k.n_my_tiles * k.sub_per_tile * k.spp;  // unit = 32 (pixel, sample) slots
-    // work counters are 32-bit: keep (slots of a batch) x (shadow rays per shaded hit) below 2^31
-    const long long slot_cap = std::max<long long>(32, (1ll << 31) / std::max(1, k.shadow_per_rec));
+    // work counters are 32-bit: keep (slots of a batch) x (shadow rays per shaded hit) below 2^31 ...
+    const long long spr = std::max(1, k.shadow_per_rec);
+    const long long slot_cap = std::max<long long>(32, (1ll << 31) / spr);
     const long long batch_units = std::max<long long>(1, std::min<long long>(std::max<long long>(total_units, 1), std::min(d->batch_slots, slot_cap) / 32));
-    int rc = ensure_buffers(d, k, batch_units * 32);
+    const int branching = ray_tree_branching(h);
+    int rc = ensure_buffers(d, k, batch_units * 32, branching);
     if (rc != RT_OK) return rc;
     k.q[0] = d->q[0]; k.q[1] = d->q[1];
     k.hit_prim = d->hit_prim;
     for (int i = 0; i < 2; ++i) { k.recs[i] = d->recs[i]; k.vis[i] = d->vis[i]; }
     k.accum = d->accum; k.lvl = d->lvl; k.totals = d->totals;
-    // all of the allocated queue space, also after a retry with smaller batches (the allocation never
-    // shrinks, so halving the batch really halves the pressure on the queues)
-    k.capacity = (int)std::min<long long>(d->capacity, (1ll << 30));
+    k.overflow_host = d->overflow_host;
+    const int grid_trace = d->sm_count * d->trace_blocks;
+    const int grid_shadow = d->sm_count * d->shadow_blocks;
+    const int grid_wide = d->sm_count * 8;
+    // ... and at deeper levels, where the record count can grow up to the queue capacity, keep
+    // capacity x (shadow rays per hit) + (what the persistent warps over-fetch past the end) below
+    // 2^32. All of the allocated queue space otherwise, also after a retry with smaller batches (the
+    // allocation never shrinks, so halving the batch really halves the pressure on the queues).
+    const long long overshoot = (long long)std::max(grid_trace, grid_shadow) * (RT_TRACE_THREADS / 32) * 128 + 65536;
+    const long long work_cap = ((1ll << 32) - overshoot) / spr;
+    k.capacity = (int)std::min<long long>(std::min<long long>(d->capacity, (1ll << 30)), work_cap);
 
     int launches = 0;
     CUDA_TRY(cudaMemsetAsync(d->lvl, 0, (RT_MAX_DEPTH + 2) * RT_LVL_STRIDE * sizeof(unsigned int), stream));
@@ -1280,7 +1472,8 @@ static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time
     clear_accum_kernel<<<(n_pix + 255) / 256, 256, 0, stream>>>(k);
     ++launches;
     d->class_of.clear();
-    const size_t max_pairs = 512;
+    const long long n_batches = total_units > 0 ? (total_units + batch_units - 1) / batch_units : 0;
+    const size_t max_pairs = time_classes ? (size_t)std::min<long long>(n_batches * (k.max_depth + 1) * 4, 1ll << 20) : 0;
     if (time_classes && d->class_ev.size() < 2 * max_pairs) {
         const size_t have = d->class_ev.size();
         d->class_ev.resize(2 * max_pairs, nullptr);
@@ -1321,9 +1514,6 @@ static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time
             CUDA_TRY(cudaEventCreateWithFlags(&d->ev_light[i], cudaEventDisableTiming));
         }
     }
-    const int grid_trace = d->sm_count * d->trace_blocks;
-    const int grid_shadow = d->sm_count * d->shadow_blocks;
-    const int grid_wide = d->sm_count * 8;
     for (long long u0 = 0; u0 < total_units; u0 += batch_units) {
         const int n_units = (int)std::min<long long>(batch_units, total_units - u0);
         gen_kernel<<<std::min(grid_wide, (n_units + 7) / 8), 256, 0, stream>>>(k, u0, n_units);
@@ -1379,16 +1569,40 @@ static int enqueue_frame(DeviceScene* d, FrameParams& k, bool collect, bool time
     ++launches;
     CUDA_TRY(cudaGetLastError());
     d->last_launches = launches;
+    d->total_launches += (unsigned long long)launches;
     return RT_OK;
 }
 
+// A queue overflow of an asynchronous frame cannot be answered by re-rendering (nobody waits for
+// the frame), so it is STICKY: the next call on the scene that looks (rt_render*, rt_scene_last_timing)
+// halves the batch, reports RT_ERR_SCENE once, and the caller renders again.
+static int report_async_overflow(DeviceScene* d) {
+    if (!d->async_pending || !*(volatile unsigned int*)d->overflow_host) return RT_OK;
+    if (cudaEventSynchronize(d->ev[2]) != cudaSuccess) cudaGetLastError();
+    *d->overflow_host = 0u;
+    d->async_pending = false;
+    d->batch_slots = std::max<long long>(32, d->batch_slots / 2);
+    set_error("an earlier asynchronous frame on this scene overflowed a ray queue and dropped rays; the batch size has been "
+              "halved: render the frame again (a synchronous call, stats != NULL, adapts the batch size by itself)");
+    return RT_ERR_SCENE;
+}
+
 static int render_impl(HostScene& h, const rt_render_params& rp, uint8_t* rgb8, int32_t* hit_ids, float* linear,
-                       cudaStream_t stream, rt_render_stats* stats) {
-    int rc = ensure_uploaded(h, stream, nullptr);
-    if (rc != RT_OK) return rc;
-    DeviceScene* d = h.dev;
+                       cudaStream_t stream, rt_render_stats* stats, bool packed = false, TilePlan** plan_out = nullptr) {
     FrameParams k;
-    if ((rc = fill_params(h, rp, k)) != RT_OK) return rc;
+    int rc = fill_params(h, rp, k);
+    if (rc != RT_OK) return rc;
+    DeviceScene* d = nullptr;
+    if ((rc = ensure_uploaded(h, stream, nullptr, &d)) != RT_OK) return rc;
+    if ((rc = report_async_overflow(d)) != RT_OK) return rc;
+    // one frame in flight per scene and device: the wavefront buffers are shared, so a frame on
+    // another stream waits for the previous one; every frame waits for the scene upload
+    if (d->timed) CUDA_TRY(cudaStreamWaitEvent(stream, d->ev[2], 0));
+    CUDA_TRY(cudaStreamWaitEvent(stream, d->ev_upload, 0));
+    TilePlan* plan = nullptr;
+    if ((rc = ensure_plan(d, k, rp.reserved[5], stream, &plan)) != RT_OK) return rc;
+    if (plan_out) *plan_out = plan;
+    k.packed = packed ? 1 : 0;
     k.bvh.prims = d->prims; k.bvh.wide = d->wide; k.bvh.leafbox = d->leafbox; k.bvh.stack_depth = d->stack_depth;
     k.mats = d->mats; k.lights = d->lights; k.textures = d->textures; k.texels = d->texels;
     k.hit_ids = hit_ids;
@@ -1396,13 +1610,15 @@ static int render_impl(HostScene& h, const rt_render_params& rp, uint8_t* rgb8, 
     for (int attempt = 0;; ++attempt) {
         CUDA_TRY(cudaEventRecord(d->ev[0], stream));
         CUDA_TRY(cudaEventRecord(d->ev[1], stream));
-        if ((rc = enqueue_frame(d, k, rp.collect_stats != 0, (rp.reserved[1] & 1) != 0, (rp.reserved[2] & 1) != 0, rgb8, linear, stream)) != RT_OK) return rc;
+        if ((rc = enqueue_frame(h, d, k, rp.collect_stats != 0, (rp.reserved[1] & 1) != 0, (rp.reserved[2] & 1) != 0, rgb8, linear, stream)) != RT_OK) return rc;
         CUDA_TRY(cudaEventRecord(d->ev[2], stream));
         d->timed = true;
-        if (!stats) return RT_OK;  // asynchronous: an overflow would be reported by the next synchronous call
+        if (!stats) { d->async_pending = true; return RT_OK; }  // asynchronous: an overflow is reported by the next call
 
         std::memset(stats, 0, sizeof(*stats));
         CUDA_TRY(cudaEventSynchronize(d->ev[2]));
+        d->async_pending = false;
+        *d->overflow_host = 0u;
         unsigned long long c[8];
         CUDA_TRY(cudaMemcpy(c, d->totals, sizeof(c), cudaMemcpyDeviceToHost));
         if (c[T_OVERFLOW] && d->batch_slots > 32 && attempt < 40) {
@@ -1421,10 +1637,12 @@ static int render_impl(HostScene& h, const rt_render_params& rp, uint8_t* rgb8, 
         CUDA_TRY(cudaEventElapsedTime(&stats->kernel_ms, d->ev[1], d->ev[2]));
         CUDA_TRY(cudaEventElapsedTime(&stats->total_ms, d->ev[0], d->ev[2]));
         stats->launches = d->last_launches;
-        stats->pixels = (int32_t)shard_pixels(k);
+        stats->pixels = (int32_t)plan->pixels;
         return RT_OK;
     }
 }
+
+static bool partial_frame(const rt_render_params& rp) { return rp.world > 1 || rp.reserved[3] != 0 || rp.reserved[4] != 0; }
 
 // rt_render: host output buffers. Upload (if the device copy is stale) -> render -> copy back, all
 // on the default stream; frame-sized device buffers are kept between calls. total_ms = CUDA-event
@@ -1445,11 +1663,12 @@ static int render_host(HostScene& h, const rt_render_params& rp, uint8_t* rgb8, 
     if (ee != cudaSuccess) { cudaEventDestroy(e0); set_error(std::string("cudaEventCreate: ") + cudaGetErrorString(ee)); return RT_ERR_CUDA; }
     auto body = [&]() -> int {
         CUDA_TRY(cudaEventRecord(e0, stream));
-        int rc = ensure_uploaded(h, stream, nullptr);
+        DeviceScene* d = nullptr;
+        int rc = ensure_uploaded(h, stream, nullptr, &d);
         if (rc != RT_OK) return rc;
-        DeviceScene* d = h.dev;
         const size_t n = (size_t)h.cam.res_x * h.cam.res_y;
         if (n > d->out_pixels) {
+            CUDA_TRY(cudaDeviceSynchronize());
             cudaFree(d->out_rgb); cudaFree(d->out_ids); cudaFree(d->out_lin);
             d->out_rgb = nullptr; d->out_ids = nullptr; d->out_lin = nullptr; d->out_pixels = 0;
             CUDA_TRY(cudaMalloc((void**)&d->out_rgb, n * 3));
@@ -1457,7 +1676,7 @@ static int render_host(HostScene& h, const rt_render_params& rp, uint8_t* rgb8, 
             CUDA_TRY(cudaMalloc((void**)&d->out_lin, n * 3 * sizeof(float)));
             d->out_pixels = n;
         }
-        if (rp.world > 1) {  // pixels outside this rank's tiles stay zero / -1 in the host buffers
+        if (partial_frame(rp)) {  // pixels outside this rank's tiles / the window stay zero / -1 in the host buffers
             if (rgb8) CUDA_TRY(cudaMemsetAsync(d->out_rgb, 0, n * 3, stream));
             if (hit_ids) CUDA_TRY(cudaMemsetAsync(d->out_ids, 0xff, n * sizeof(int32_t), stream));
             if (linear) CUDA_TRY(cudaMemsetAsync(d->out_lin, 0, n * 3 * sizeof(float), stream));
@@ -1480,6 +1699,261 @@ static int render_host(HostScene& h, const rt_render_params& rp, uint8_t* rgb8, 
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rt_render_multi: one process, N GPUs. The reference's frame loop (raytracer.cpp:433-476) is one
+// serial loop over pixels; pixels are independent, so the frame is dealt to the GPUs by screen
+// tiles (scene + BVH replicated, no inter-GPU traffic in the render loop). One persistent host
+// thread per GPU: upload (all GPUs copy from the same page-locked staging buffer, in parallel) ->
+// render its tiles into a PACKED buffer (tile-major over the tiles it owns) -> one D2H copy per
+// output into page-locked memory -> scatter the tile rows into the caller's frame.
+// ---------------------------------------------------------------------------------------------
+struct MultiJob {
+    HostScene* h = nullptr;
+    rt_render_params rp{};
+    uint8_t* rgb8 = nullptr;
+    int32_t* hit_ids = nullptr;
+    float* linear = nullptr;
+};
+
+struct MultiWorker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    int device = 0;
+    bool has_job = false, done = false, quit = false;
+    MultiJob job;
+    int rc = RT_OK;
+    std::string err;
+    rt_render_stats stats{};
+};
+
+struct MultiGpu {
+    std::vector<MultiWorker*> workers;
+};
+
+// Copies this device's packed tiles from the landing zone into the caller's frame.
+template <typename T>
+static void scatter_tiles(const FrameParams& k, const TilePlan& plan, const T* packed, T* frame, int channels) {
+    for (size_t i = 0; i < plan.tiles.size(); ++i) {
+        const int t = plan.tiles[i], tx = t % k.tiles_x, ty = t / k.tiles_x;
+        const int x0 = std::max(tx * k.tile_w, k.win_x0), x1 = std::min((tx + 1) * k.tile_w, k.win_x1);
+        const int y0 = std::max(ty * k.tile_h, k.win_y0), y1 = std::min((ty + 1) * k.tile_h, k.win_y1);
+        for (int y = y0; y < y1; ++y) {
+            const T* src = packed + (((size_t)i * k.tile_h + (y - ty * k.tile_h)) * k.tile_w + (x0 - tx * k.tile_w)) * channels;
+            std::memcpy(frame + ((size_t)y * k.res_x + x0) * channels, src, (size_t)(x1 - x0) * channels * sizeof(T));
+        }
+    }
+}
+
+static int multi_render_shard(const MultiJob& job, rt_render_stats* stats) {
+    HostScene& h = *job.h;
+    FrameParams k;
+    int rc = fill_params(h, job.rp, k);
+    if (rc != RT_OK) return rc;
+    DeviceScene* d = nullptr;
+    if ((rc = device_scene(h, &d)) != RT_OK) return rc;
+    if (!d->own) CUDA_TRY(cudaStreamCreateWithFlags(&d->own, cudaStreamNonBlocking));
+    const cudaStream_t stream = d->own;
+    if ((rc = ensure_uploaded(h, stream, nullptr, &d)) != RT_OK) return rc;
+    // worst case of a shard: every tile of the frame (world = 1)
+    const size_t cap = (size_t)k.n_tiles * k.tile_w * k.tile_h;
+    if (cap > d->out_pixels) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(d->out_rgb); cudaFree(d->out_ids); cudaFree(d->out_lin);
+        d->out_rgb = nullptr; d->out_ids = nullptr; d->out_lin = nullptr; d->out_pixels = 0;
+        CUDA_TRY(cudaMalloc((void**)&d->out_rgb, cap * 3));
+        CUDA_TRY(cudaMalloc((void**)&d->out_ids, cap * sizeof(int32_t)));
+        CUDA_TRY(cudaMalloc((void**)&d->out_lin, cap * 3 * sizeof(float)));
+        d->out_pixels = cap;
+    }
+    if (cap > d->host_pixels) {
+        if (d->host_rgb) cudaFreeHost(d->host_rgb);
+        if (d->host_ids) cudaFreeHost(d->host_ids);
+        if (d->host_lin) cudaFreeHost(d->host_lin);
+        d->host_rgb = nullptr; d->host_ids = nullptr; d->host_lin = nullptr; d->host_pixels = 0;
+        CUDA_TRY(cudaHostAlloc((void**)&d->host_rgb, cap * 3, cudaHostAllocDefault));
+        CUDA_TRY(cudaHostAlloc((void**)&d->host_ids, cap * sizeof(int32_t), cudaHostAllocDefault));
+        CUDA_TRY(cudaHostAlloc((void**)&d->host_lin, cap * 3 * sizeof(float), cudaHostAllocDefault));
+        d->host_pixels = cap;
+    }
+    TilePlan* plan = nullptr;
+    rt_render_stats local;
+    rc = render_impl(h, job.rp, job.rgb8 ? d->out_rgb : nullptr, job.hit_ids ? d->out_ids : nullptr, job.linear ? d->out_lin : nullptr,
+                     stream, &local, true, &plan);
+    if (rc != RT_OK) return rc;
+    const size_t n = plan->tiles.size() * (size_t)k.tile_w * k.tile_h;
+    if (n > 0) {
+        if (job.rgb8) CUDA_TRY(cudaMemcpyAsync(d->host_rgb, d->out_rgb, n * 3, cudaMemcpyDeviceToHost, stream));
+        if (job.hit_ids) CUDA_TRY(cudaMemcpyAsync(d->host_ids, d->out_ids, n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        if (job.linear) CUDA_TRY(cudaMemcpyAsync(d->host_lin, d->out_lin, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if (job.rgb8) scatter_tiles<uint8_t>(k, *plan, d->host_rgb, job.rgb8, 3);
+        if (job.hit_ids) scatter_tiles<int32_t>(k, *plan, d->host_ids, job.hit_ids, 1);
+        if (job.linear) scatter_tiles<float>(k, *plan, d->host_lin, job.linear, 3);
+    }
+    *stats = local;
+    return RT_OK;
+}
+
+static void multi_worker_main(MultiWorker* w) {
+    cudaSetDevice(w->device);
+    std::unique_lock<std::mutex> lock(w->mu);
+    while (true) {
+        w->cv.wait(lock, [w] { return w->has_job || w->quit; });
+        if (w->quit) return;
+        MultiJob job = w->job;
+        lock.unlock();
+        rt_render_stats st;
+        std::memset(&st, 0, sizeof(st));
+        const int rc = multi_render_shard(job, &st);
+        lock.lock();
+        w->rc = rc;
+        w->err = rc == RT_OK ? std::string() : std::string(rt_last_error());
+        w->stats = st;
+        w->has_job = false;
+        w->done = true;
+        w->cv.notify_all();
+    }
+}
+
+static void multi_shutdown(MultiGpu* m) {
+    if (!m) return;
+    for (MultiWorker* w : m->workers) {
+        { std::lock_guard<std::mutex> lock(w->mu); w->quit = true; }
+        w->cv.notify_all();
+        if (w->th.joinable()) w->th.join();
+        delete w;
+    }
+    delete m;
+}
+
+static int render_multi(HostScene& h, const rt_render_params& rp_in, int n_devices, const int32_t* devices, uint8_t* rgb8,
+                        int32_t* hit_ids, float* linear, rt_render_stats* stats) {
+    const auto t0 = std::chrono::steady_clock::now();
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: the renderer has no CPU fallback");
+        return RT_ERR_CUDA;
+    }
+    if (n_devices < 1 || n_devices > count) { set_error("rt_render_multi: n_devices must be in [1, rt_device_count()]"); return RT_ERR_INVALID; }
+    if (rp_in.world != 1 || rp_in.rank != 0) { set_error("rt_render_multi: rank/world must be 0/1 (the call deals the tiles itself)"); return RT_ERR_INVALID; }
+    std::vector<int> ids((size_t)n_devices);
+    for (int i = 0; i < n_devices; ++i) {
+        ids[i] = devices ? devices[i] : i;
+        if (ids[i] < 0 || ids[i] >= count) { set_error("rt_render_multi: device ordinal out of range"); return RT_ERR_INVALID; }
+        for (int j = 0; j < i; ++j) if (ids[j] == ids[i]) { set_error("rt_render_multi: a device is listed twice"); return RT_ERR_INVALID; }
+    }
+    {
+        FrameParams probe;
+        const int rc = fill_params(h, rp_in, probe);
+        if (rc != RT_OK) return rc;
+    }
+    int rc = ensure_staging(h);
+    if (rc != RT_OK) return rc;
+    DeviceSet* set = h.dev;
+    if (!set->multi) set->multi = new MultiGpu();
+    MultiGpu* m = set->multi;
+    // workers are bound to a device for life; find or start the one of each requested device
+    std::vector<MultiWorker*> use;
+    for (int dev : ids) {
+        MultiWorker* w = nullptr;
+        for (MultiWorker* c : m->workers) if (c->device == dev) w = c;
+        if (!w) {
+            w = new MultiWorker();
+            w->device = dev;
+            w->th = std::thread(multi_worker_main, w);
+            m->workers.push_back(w);
+        }
+        use.push_back(w);
+    }
+    // pixels no device renders (outside the window) keep the "nothing rendered" values of rt_render
+    if (rp_in.reserved[3] != 0 || rp_in.reserved[4] != 0) {
+        const size_t n = (size_t)h.cam.res_x * h.cam.res_y;
+        if (rgb8) std::memset(rgb8, 0, n * 3);
+        if (hit_ids) std::memset(hit_ids, 0xff, n * sizeof(int32_t));
+        if (linear) std::memset(linear, 0, n * 3 * sizeof(float));
+    }
+    for (int i = 0; i < n_devices; ++i) {
+        MultiWorker* w = use[i];
+        std::lock_guard<std::mutex> lock(w->mu);
+        w->job.h = &h;
+        w->job.rp = rp_in;
+        w->job.rp.rank = i;
+        w->job.rp.world = n_devices;
+        w->job.rgb8 = rgb8; w->job.hit_ids = hit_ids; w->job.linear = linear;
+        w->done = false;
+        w->has_job = true;
+        w->cv.notify_all();
+    }
+    rt_render_stats total;
+    std::memset(&total, 0, sizeof(total));
+    int first_rc = RT_OK;
+    std::string first_err;
+    for (MultiWorker* w : use) {
+        std::unique_lock<std::mutex> lock(w->mu);
+        w->cv.wait(lock, [w] { return w->done; });
+        if (w->rc != RT_OK && first_rc == RT_OK) { first_rc = w->rc; first_err = "device " + std::to_string(w->device) + ": " + w->err; }
+        total.rays += w->stats.rays; total.primary_rays += w->stats.primary_rays; total.shadow_rays += w->stats.shadow_rays;
+        total.secondary_rays += w->stats.secondary_rays; total.node_visits += w->stats.node_visits; total.prim_tests += w->stats.prim_tests;
+        total.kernel_ms = std::max(total.kernel_ms, w->stats.kernel_ms);
+        total.launches += w->stats.launches;
+        total.pixels += w->stats.pixels;
+    }
+    if (first_rc != RT_OK) { set_error(first_err); return first_rc; }
+    total.total_ms = (float)(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e3);
+    if (stats) *stats = total;
+    return RT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Traversal ceiling: trav_step -- the very code of the traversal loop -- with all 32 lanes of every
+// warp busy on nodes that stay in L1 (the top `n_nodes` nodes of the scene's own tree, visited round
+// robin; the stack is reset after every step). Box tests per second of that loop on this chip is
+// what the traversal kernels would reach without divergence, cache misses, fetch / primitive
+// phases: the denominator of bench.py's roofline.
+// ---------------------------------------------------------------------------------------------
+template <bool ANY>
+__global__ void __launch_bounds__(RT_TRACE_THREADS, RT_TRACE_MINBLOCKS) trav_peak_kernel(BvhView bvh, int n_nodes, int steps, float3 eye, float3 lo, float3 hi,
+                                                                                            unsigned long long* out) {
+    const unsigned int words = ANY ? 1u : (unsigned int)RT_STACK_WORDS;
+    const unsigned int stride = blockDim.x * words * (unsigned int)sizeof(int);
+    TravState s;
+    s.sp0 = (unsigned int)__cvta_generic_to_shared(rt_stack_smem + threadIdx.x * words);
+    s.sp_end = s.sp0 + (unsigned int)bvh.stack_depth * stride;
+    const unsigned int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    // a ray from the eye into the scene box (never axis-parallel)
+    const U4 u = philox4x32_10(U4{gid, 0x77u, 0u, 0u}, 0x9E3779B9u, 0xBB67AE85u);
+    Ray r;
+    r.ox = eye.x; r.oy = eye.y; r.oz = eye.z;
+    r.dx = lo.x + (hi.x - lo.x) * u32_to_unit_float(u.x) - eye.x;
+    r.dy = lo.y + (hi.y - lo.y) * u32_to_unit_float(u.y) - eye.y;
+    r.dz = lo.z + (hi.z - lo.z) * u32_to_unit_float(u.z) - eye.z;
+    if (fabsf(r.dx) < 1e-3f) r.dx = 1e-3f;
+    if (fabsf(r.dy) < 1e-3f) r.dy = 1e-3f;
+    if (fabsf(r.dz) < 1e-3f) r.dz = 1e-3f;
+    normalize3(r.dx, r.dy, r.dz);
+    r.time = 0.0f;
+    TraceStats st = {0u, 0u};
+    BvhView b = bvh;
+    b.prune = 1;
+    b.use_bvh = 1;
+    trav_begin<ANY>(b, s, r, 1e30f, st);
+    unsigned long long acc = 0;
+    int node = (int)(gid % (unsigned int)n_nodes);
+#pragma unroll 1
+    for (int i = 0; i < steps; ++i) {
+        s.cur = node;
+        s.sp = s.sp0;
+        s.pend = 0u;
+        trav_step<ANY, false>(b, s, stride, st);
+        acc += (unsigned int)s.cur + s.pend + (s.sp - s.sp0);
+        node = node + 1 == n_nodes ? 0 : node + 1;
+    }
+    if (acc == 0x1234567887654321ull) out[1] = acc;  // keeps the loop alive
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = (unsigned long long)gridDim.x * blockDim.x * (unsigned long long)steps * 4ull;
 }
 
 }  // namespace rtb
@@ -1506,9 +1980,17 @@ int rt_scene_evict(rt_scene* scene) {
     return RT_OK;
 }
 
+static rtb::DeviceScene* current_device_scene(rt_scene* scene) {
+    rtb::DeviceSet* set = rtb::host_of(scene)->dev;
+    int dev = 0;
+    if (!set || cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    std::lock_guard<std::mutex> lock(set->mu);
+    return dev < (int)set->devs.size() ? set->devs[dev] : nullptr;
+}
+
 int rt_scene_last_timing(rt_scene* scene, float* kernel_ms, float* total_ms) {
     if (!scene) { rtb::set_error("null scene"); return RT_ERR_INVALID; }
-    rtb::DeviceScene* d = rtb::host_of(scene)->dev;
+    rtb::DeviceScene* d = current_device_scene(scene);
     if (!d || !d->timed) { rtb::set_error("rt_scene_last_timing: no render has been recorded on this scene"); return RT_ERR_INVALID; }
     cudaError_t e = cudaEventSynchronize(d->ev[2]);
     float k = 0.0f, t = 0.0f;
@@ -1516,12 +1998,9 @@ int rt_scene_last_timing(rt_scene* scene, float* kernel_ms, float* total_ms) {
     if (e == cudaSuccess) e = cudaEventElapsedTime(&t, d->ev[0], d->ev[2]);
     if (e != cudaSuccess) { rtb::set_error(std::string("rt_scene_last_timing: ") + cudaGetErrorString(e)); return RT_ERR_CUDA; }
     // an asynchronous frame cannot re-render itself when a ray queue overflows: report it here
-    unsigned long long overflow = 0;
-    if (cudaMemcpy(&overflow, d->totals + rtb::T_OVERFLOW, sizeof(overflow), cudaMemcpyDeviceToHost) == cudaSuccess && overflow) {
-        rtb::set_error("the last frame overflowed a ray queue and dropped rays: render once synchronously (stats != NULL) so that the "
-                       "batch size adapts to this scene");
-        return RT_ERR_SCENE;
-    }
+    const int rc = rtb::report_async_overflow(d);
+    if (rc != RT_OK) return rc;
+    d->async_pending = false;  // finished, looked at, clean
     if (kernel_ms) *kernel_ms = k;
     if (total_ms) *total_ms = t;
     return RT_OK;
@@ -1529,7 +2008,7 @@ int rt_scene_last_timing(rt_scene* scene, float* kernel_ms, float* total_ms) {
 
 int rt_scene_last_kernel_times(rt_scene* scene, float* ms4, int32_t* launches4, int32_t* frame_launches4) {
     if (!scene) { rtb::set_error("null scene"); return RT_ERR_INVALID; }
-    rtb::DeviceScene* d = rtb::host_of(scene)->dev;
+    rtb::DeviceScene* d = current_device_scene(scene);
     if (!d || !d->timed) { rtb::set_error("rt_scene_last_kernel_times: no render has been recorded on this scene"); return RT_ERR_INVALID; }
     float ms[4] = {0, 0, 0, 0};
     int32_t n[4] = {0, 0, 0, 0};
@@ -1550,12 +2029,28 @@ int rt_scene_last_kernel_times(rt_scene* scene, float* ms4, int32_t* launches4, 
     return RT_OK;
 }
 
+int rt_scene_launch_count(rt_scene* scene, uint64_t* launches) {
+    if (!scene || !launches) { rtb::set_error("null argument"); return RT_ERR_INVALID; }
+    *launches = 0;
+    rtb::DeviceSet* set = rtb::host_of(scene)->dev;
+    if (!set) return RT_OK;
+    std::lock_guard<std::mutex> lock(set->mu);
+    for (rtb::DeviceScene* d : set->devs) if (d) *launches += d->total_launches;
+    return RT_OK;
+}
+
+static int selftest_grid() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cudaGetLastError(); return 1184; }
+    return std::max(1, sms) * 8;
+}
+
 int rt_selftest_boxes(uint64_t seed, int64_t n, uint64_t* out8) {
     if (!out8 || n <= 0) { rtb::set_error("rt_selftest_boxes: bad argument"); return RT_ERR_INVALID; }
     unsigned long long* d = nullptr;
     if (cudaMalloc((void**)&d, 8 * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); rtb::set_error("no CUDA device"); return RT_ERR_CUDA; }
     cudaMemset(d, 0, 8 * sizeof(unsigned long long));
-    rtb::selftest_box_kernel<<<148 * 8, 256>>>((uint32_t)seed, (long long)n, d);
+    rtb::selftest_box_kernel<<<selftest_grid(), 256>>>((uint32_t)seed, (long long)n, d);
     const cudaError_t e = cudaMemcpy(out8, d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) { rtb::set_error(std::string("rt_selftest_boxes: ") + cudaGetErrorString(e)); return RT_ERR_CUDA; }
@@ -1565,11 +2060,12 @@ int rt_selftest_boxes(uint64_t seed, int64_t n, uint64_t* out8) {
 int rt_selftest_cull(rt_scene* scene, uint64_t seed, int32_t rays_per_primitive, uint64_t* out8) {
     if (!scene || !out8 || rays_per_primitive <= 0) { rtb::set_error("rt_selftest_cull: bad argument"); return RT_ERR_INVALID; }
     rtb::HostScene& h = *rtb::host_of(scene);
-    int rc = rtb::ensure_uploaded(h, 0, nullptr);
+    rtb::DeviceScene* ds = nullptr;
+    int rc = rtb::ensure_uploaded(h, 0, nullptr, &ds);
     if (rc != RT_OK) return rc;
     rtb::BvhView b;
     std::memset(&b, 0, sizeof(b));
-    b.prims = h.dev->prims; b.wide = h.dev->wide; b.leafbox = h.dev->leafbox; b.n_prims = (int)h.dprims.size(); b.use_bvh = 1; b.prune = 1;
+    b.prims = ds->prims; b.wide = ds->wide; b.leafbox = ds->leafbox; b.n_prims = (int)h.dprims.size(); b.use_bvh = 1; b.prune = 1;
     float span = 1.0f;
     if (!h.tree.empty())
         for (int a = 0; a < 3; ++a) span = std::max(span, h.tree[0].box.hi[a] - h.tree[0].box.lo[a]);
@@ -1577,11 +2073,64 @@ int rt_selftest_cull(rt_scene* scene, uint64_t seed, int32_t rays_per_primitive,
     unsigned long long* d = nullptr;
     if (cudaMalloc((void**)&d, 8 * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); rtb::set_error("cudaMalloc failed"); return RT_ERR_CUDA; }
     cudaMemset(d, 0, 8 * sizeof(unsigned long long));
-    rtb::selftest_cull_kernel<<<148 * 8, 256>>>(b, (int)h.dwide.size(), rays_per_primitive, (uint32_t)seed, span, d);
+    rtb::selftest_cull_kernel<<<selftest_grid(), 256>>>(b, (int)h.dwide.size(), rays_per_primitive, (uint32_t)seed, span, d);
     const cudaError_t e = cudaMemcpy(out8, d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) { rtb::set_error(std::string("rt_selftest_cull: ") + cudaGetErrorString(e)); return RT_ERR_CUDA; }
     return RT_OK;
+}
+
+int rt_traversal_peak(rt_scene* scene, int32_t any_hit, int32_t n_nodes, int32_t steps, int32_t repeats, double* box_tests_per_s, float* ms) {
+    if (!scene || !box_tests_per_s || n_nodes < 1 || steps < 1 || repeats < 1) { rtb::set_error("rt_traversal_peak: bad argument"); return RT_ERR_INVALID; }
+    rtb::HostScene& h = *rtb::host_of(scene);
+    if (h.dwide.empty()) { rtb::set_error("rt_traversal_peak: the scene has no shapes"); return RT_ERR_SCENE; }
+    rtb::DeviceScene* ds = nullptr;
+    int rc = rtb::ensure_uploaded(h, 0, nullptr, &ds);
+    if (rc != RT_OK) return rc;
+    rtb::BvhView b;
+    std::memset(&b, 0, sizeof(b));
+    b.prims = ds->prims; b.wide = ds->wide; b.leafbox = ds->leafbox; b.n_prims = (int)h.dprims.size(); b.use_bvh = 1; b.prune = 1;
+    b.stack_depth = ds->stack_depth;
+    // inner nodes only (a leaf node parks its children in `pend` instead of pushing): the first n nodes in
+    // breadth-first order are the top of the tree
+    int n = 0;
+    const int limit = std::min<int>(n_nodes, (int)h.dwide.size());
+    while (n < limit && !(((const uint32_t*)h.dwide[n].f)[25] & rtb::WIDE_LEAF)) ++n;
+    if (n < 1) n = 1;
+    const rtb::Box& box = h.tree[0].box;
+    const float3 eye = make_float3(h.cam.location[0], h.cam.location[1], h.cam.location[2]);
+    const float3 lo = make_float3(box.lo[0], box.lo[1], box.lo[2]), hi = make_float3(box.hi[0], box.hi[1], box.hi[2]);
+    unsigned long long* d = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto body = [&]() -> int {
+        CUDA_TRY(cudaMalloc((void**)&d, 2 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaEventCreate(&e0));
+        CUDA_TRY(cudaEventCreate(&e1));
+        const int grid = ds->sm_count * (any_hit ? ds->shadow_blocks : ds->trace_blocks);
+        double best = 0.0;
+        float best_ms = 0.0f;
+        for (int r = 0; r < repeats + 1; ++r) {  // first launch = warm-up
+            CUDA_TRY(cudaEventRecord(e0, 0));
+            if (any_hit) rtb::trav_peak_kernel<true><<<grid, RT_TRACE_THREADS, ds->stack_bytes>>>(b, n, steps, eye, lo, hi, d);
+            else rtb::trav_peak_kernel<false><<<grid, RT_TRACE_THREADS, ds->stack_bytes>>>(b, n, steps, eye, lo, hi, d);
+            CUDA_TRY(cudaEventRecord(e1, 0));
+            CUDA_TRY(cudaEventSynchronize(e1));
+            float t = 0.0f;
+            CUDA_TRY(cudaEventElapsedTime(&t, e0, e1));
+            unsigned long long tests = 0;
+            CUDA_TRY(cudaMemcpy(&tests, d, sizeof(tests), cudaMemcpyDeviceToHost));
+            if (r > 0 && t > 0.0f && (double)tests / (t * 1e-3) > best) { best = (double)tests / (t * 1e-3); best_ms = t; }
+        }
+        *box_tests_per_s = best;
+        if (ms) *ms = best_ms;
+        return RT_OK;
+    };
+    rc = body();
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(d);
+    return rc;
 }
 
 int rt_shard_pixels(const rt_scene* scene, const rt_render_params* p, int64_t* n_pixels) {
@@ -1589,7 +2138,10 @@ int rt_shard_pixels(const rt_scene* scene, const rt_render_params* p, int64_t* n
     rtb::FrameParams k;
     int rc = rtb::fill_params(*rtb::host_of(scene), *p, k);
     if (rc != RT_OK) return rc;
-    *n_pixels = rtb::shard_pixels(k);
+    std::vector<int> tiles;
+    int64_t pixels = 0;
+    rtb::plan_tiles(k, p->reserved[5], tiles, pixels);
+    *n_pixels = pixels;
     return RT_OK;
 }
 
@@ -1603,6 +2155,12 @@ int rt_render(rt_scene* scene, const rt_render_params* p, uint8_t* rgb8, int32_t
               rt_render_stats* stats) {
     if (!scene || !p) { rtb::set_error("null argument"); return RT_ERR_INVALID; }
     return rtb::render_host(*rtb::host_of(scene), *p, rgb8, hit_ids, linear, stats);
+}
+
+int rt_render_multi(rt_scene* scene, const rt_render_params* p, int32_t n_devices, const int32_t* devices, uint8_t* rgb8,
+                    int32_t* hit_ids, float* linear, rt_render_stats* stats) {
+    if (!scene || !p) { rtb::set_error("null argument"); return RT_ERR_INVALID; }
+    return rtb::render_multi(*rtb::host_of(scene), *p, n_devices, devices, rgb8, hit_ids, linear, stats);
 }
 
 }  // extern "C"

@@ -25,7 +25,7 @@ const HostScene* rtb::host_of(const rt_scene* s) { return &s->host; }
 extern "C" {
 
 const char* rt_last_error(void) { return rtb::g_last_error.c_str(); }
-int rt_version(void) { return 1; }
+int rt_version(void) { return 2; }
 
 void rt_render_params_default(rt_render_params* p) {
     if (!p) return;

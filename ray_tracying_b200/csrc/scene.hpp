@@ -92,7 +92,7 @@ struct TreeNode {
     int first = 0, count = 0;   // range over the sorted order
 };
 
-struct DeviceScene;  // defined in render.cu
+struct DeviceSet;  // defined in render.cu: the scene's copies on the CUDA devices
 
 struct HostScene {
     rt_camera_desc cam{};
@@ -117,7 +117,7 @@ struct HostScene {
     std::vector<DTexture> dtextures;
     std::vector<uint8_t> texels;
 
-    DeviceScene* dev = nullptr;
+    DeviceSet* dev = nullptr;
 
     double build_seconds = 0.0;
 };

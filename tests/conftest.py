@@ -55,6 +55,18 @@ def lsb_agreement(a: np.ndarray, b: np.ndarray, tol: int = 1) -> float:
     return float((d <= tol).mean())
 
 
+def linear_mismatch(a: np.ndarray, b: np.ndarray, spp: int = 1) -> float:
+    """Largest |a - b| in units of the allowed bound for float images that took the same sample paths.
+    The paths' colours agree to a few ulp (powf in the specular term is the only non-IEEE operation);
+    the reference then adds its spp samples in float (up to spp * 2^-24 relative), the CUDA path adds them
+    exactly (64-bit fixed point) -- hence a RELATIVE bound that grows with spp, plus 2e-7 absolute for
+    channels near zero. <= 1 passes."""
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    bound = (2e-6 + 1.2e-7 * spp) * np.maximum(np.abs(a), np.abs(b)) + 2e-7
+    return float((np.abs(a - b) / bound).max()) if a.size else 0.0
+
+
 def rmse(a: np.ndarray, b: np.ndarray) -> float:
     return float(np.sqrt(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)))
 

@@ -31,3 +31,27 @@ def test_reference_arm_other_ranks_exit_quietly():
                         "--warmup", "1", "--workload", "ascii"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env,
                        timeout=600)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_pure_python_helpers_do_not_load_the_product_library():
+    """The reference arm imports ray_tracying_b200.workloads / .scenes: that must not map librt_b200.so
+    (the driver records which native libraries each arm loaded)."""
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import ray_tracying_b200.workloads, ray_tracying_b200.scenes, ray_tracying_b200.dist\n"
+            "assert 'ray_tracying_b200._lib' not in sys.modules and 'ray_tracying_b200.api' not in sys.modules\n"
+            "assert 'librt_b200' not in open('/proc/self/maps').read()\n"
+            "import ray_tracying_b200 as rt; rt.make_params\n"
+            "assert 'librt_b200' in open('/proc/self/maps').read()\n") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_reference_arm_sample_is_a_window_of_the_named_workload():
+    """The reference arm of a heavy workload renders windows (rows x columns) sized from a ray-count probe."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--workload", "mixed100k"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900,
+                       env=dict(os.environ, RT_BENCH_CACHE="/tmp/rt_b200_bench"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][-1])
+    assert d["config"]["name"] == "mixed100k" and "windows of" in d["config"]["sample"]
+    assert d["rays_per_step"] > 100000 and 0.05 < d["value"] < 1000
