@@ -17,6 +17,8 @@
 #include <chrono>
 #include <cstring>
 #include <future>
+#include <mutex>
+#include <string>
 #include <stdexcept>
 
 #include "scene.hpp"
@@ -209,59 +211,229 @@ void set_child_box(DWide& w, int c, const Box& b) {
     w.f[16 + c] = b.lo[2]; w.f[20 + c] = b.hi[2];
 }
 
-// Fills wide node `me` (already allocated) for reference tree node `ti`. Children of an inner
-// node get consecutive indices, allocated before descending into them.
-void emit_wide(HostScene& s, int ti, int me, int level, double scene_g) {
-    s.wide_depth = std::max(s.wide_depth, level);
-    DWide w = empty_wide();
-    const TreeNode& t = s.tree[ti];
-    if (t.left < 0) {
-        // reference leaf: children = its primitives (consecutive sorted positions) with culling boxes
-        uint32_t meta = WIDE_LEAF;
-        float qmax = 0.0f;
-        for (int k = 0; k < t.count; ++k) {
-            const HostPrim& p = s.prims[s.order[t.first + k]];
-            Box cb;
-            double pad = 0.0;
-            float q = 0.0f;
-            if (cull_pad(p, scene_g, pad, q)) {
-                for (int a = 0; a < 3; ++a) {
-                    cb.lo[a] = std::nextafter((float)((double)p.box.lo[a] - pad), -FLT_MAX);
-                    cb.hi[a] = std::nextafter((float)((double)p.box.hi[a] + pad), FLT_MAX);
-                }
-            } else {
-                for (int a = 0; a < 3; ++a) { cb.lo[a] = -1e30f; cb.hi[a] = 1e30f; }
-                q = 0.0f;
-            }
-            set_child_box(w, k, cb);
-            meta |= (1u << k) | ((uint32_t)p.type << (16 + 2 * k));
-            qmax = std::max(qmax, q);
+// ---------------------------------------------------------------------------------------------
+// The device tree. Its LEAVES are the reference's leaves (<= 4 shapes each, acceleration.cpp:29-33):
+// a shape may only be tested if the exact box of its reference leaf passes AABB::intersect, so the
+// leaf partition and the leaf boxes are the reference's. Everything ABOVE the
+// leaves is ours -- the result (min t, first shape among equal t) does not depend on how the leaves
+// are grouped -- so the upper levels are built for traversal cost:
+//   RT_B200_TREE=sah (default): binary tree over the leaves by binned surface-area heuristic
+//       (16 bins per axis on the leaf-box centroids, cost = SA_left * n_left + SA_right * n_right),
+//       collapsed to 4 children per node by repeatedly opening the child with the largest area;
+//   RT_B200_TREE=median: the reference's own median-split tree with every other level skipped.
+// Nodes are numbered breadth-first, the children of a node consecutively (index = first + slot).
+// ---------------------------------------------------------------------------------------------
+struct UpNode {
+    Box box;
+    int left = -1, right = -1;  // UpNode indices; -1 for a leaf
+    int ref_leaf = -1;          // index into HostScene::tree of the reference leaf (leaves only)
+};
+
+inline double half_area(const Box& b) {
+    const double x = (double)b.hi[0] - b.lo[0], y = (double)b.hi[1] - b.lo[1], z = (double)b.hi[2] - b.lo[2];
+    return x * y + y * z + z * x;
+}
+inline void box_reset(Box& b) { for (int i = 0; i < 3; ++i) { b.lo[i] = FLT_MAX; b.hi[i] = -FLT_MAX; } }
+inline void box_merge(Box& b, const Box& o) {
+    for (int i = 0; i < 3; ++i) { b.lo[i] = std::min(b.lo[i], o.lo[i]); b.hi[i] = std::max(b.hi[i], o.hi[i]); }
+}
+
+struct SahBuilder {
+    const HostScene& s;
+    std::vector<int> leaves;      // reference leaf (tree index) per position, permuted in place
+    std::vector<UpNode> nodes;
+    std::mutex mu;                // guards `nodes` growth when sub-trees are built on other threads
+
+    int alloc() {
+        std::lock_guard<std::mutex> lock(mu);
+        nodes.emplace_back();
+        return (int)nodes.size() - 1;
+    }
+    void set(int id, const UpNode& n) {
+        std::lock_guard<std::mutex> lock(mu);
+        nodes[id] = n;
+    }
+
+    // builds the sub-tree over leaves[lo, hi) and returns its node id
+    int build(int lo, int hi, int par_depth) {
+        const int me = alloc();
+        UpNode n;
+        box_reset(n.box);
+        for (int k = lo; k < hi; ++k) box_merge(n.box, s.tree[leaves[k]].box);
+        if (hi - lo == 1) {
+            n.ref_leaf = leaves[lo];
+            set(me, n);
+            return me;
         }
-        w.f[24] = bits_f((uint32_t)t.first);
-        w.f[25] = bits_f(meta);
-        w.f[26] = qmax;
-        s.dwide[me] = w;
-        return;
+        // binned SAH over the centroids of the leaf boxes
+        constexpr int NB = 16;
+        Box cb;
+        box_reset(cb);
+        for (int k = lo; k < hi; ++k) {
+            const Box& b = s.tree[leaves[k]].box;
+            for (int a = 0; a < 3; ++a) {
+                const float c = 0.5f * (b.lo[a] + b.hi[a]);
+                cb.lo[a] = std::min(cb.lo[a], c);
+                cb.hi[a] = std::max(cb.hi[a], c);
+            }
+        }
+        int best_axis = -1, best_bin = -1;
+        double best_cost = 1e300;
+        for (int a = 0; a < 3; ++a) {
+            const float ext = cb.hi[a] - cb.lo[a];
+            if (!(ext > 0.0f) || !(ext < 1e30f)) continue;
+            Box bins[NB];
+            int cnt[NB];
+            for (int b = 0; b < NB; ++b) { box_reset(bins[b]); cnt[b] = 0; }
+            const float scale = (float)NB / ext;
+            for (int k = lo; k < hi; ++k) {
+                const Box& b = s.tree[leaves[k]].box;
+                const int bi = std::min(NB - 1, std::max(0, (int)((0.5f * (b.lo[a] + b.hi[a]) - cb.lo[a]) * scale)));
+                box_merge(bins[bi], b);
+                cnt[bi]++;
+            }
+            double right_area[NB];
+            int right_cnt[NB];
+            Box acc;
+            box_reset(acc);
+            int c = 0;
+            for (int b = NB - 1; b >= 1; --b) {
+                if (cnt[b]) box_merge(acc, bins[b]);
+                c += cnt[b];
+                right_area[b] = c ? half_area(acc) : 0.0;
+                right_cnt[b] = c;
+            }
+            box_reset(acc);
+            c = 0;
+            for (int b = 0; b + 1 < NB; ++b) {
+                if (cnt[b]) box_merge(acc, bins[b]);
+                c += cnt[b];
+                if (c == 0 || right_cnt[b + 1] == 0) continue;
+                const double cost = half_area(acc) * c + right_area[b + 1] * right_cnt[b + 1];
+                if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b; }
+            }
+        }
+        int mid = (lo + hi) / 2;
+        if (best_axis >= 0) {
+            const int a = best_axis;
+            const float scale = (float)NB / (cb.hi[a] - cb.lo[a]);
+            auto it = std::partition(leaves.begin() + lo, leaves.begin() + hi, [&](int t) {
+                const Box& b = s.tree[t].box;
+                return std::min(NB - 1, std::max(0, (int)((0.5f * (b.lo[a] + b.hi[a]) - cb.lo[a]) * scale))) <= best_bin;
+            });
+            mid = (int)(it - leaves.begin());
+        }
+        if (mid <= lo || mid >= hi) mid = (lo + hi) / 2;  // all centroids equal: split the (position-ordered) run in half
+        if (par_depth > 0 && hi - lo > (1 << 14)) {
+            auto fut = std::async(std::launch::async, [this, lo, mid, par_depth] { return build(lo, mid, par_depth - 1); });
+            n.right = build(mid, hi, par_depth - 1);
+            n.left = fut.get();
+        } else {
+            n.left = build(lo, mid, 0);
+            n.right = build(mid, hi, 0);
+        }
+        set(me, n);
+        return me;
     }
-    int slots[4], n = 0;
-    for (int child : {t.left, t.right}) {
-        const TreeNode& c = s.tree[child];
-        if (c.left >= 0) { slots[n++] = c.left; slots[n++] = c.right; }
-        else slots[n++] = child;
+};
+
+// The reference's own tree as an UpNode tree (RT_B200_TREE=median).
+int median_upper(const HostScene& s, int ti, std::vector<UpNode>& nodes) {
+    const int me = (int)nodes.size();
+    nodes.emplace_back();
+    UpNode n;
+    n.box = s.tree[ti].box;
+    if (s.tree[ti].left < 0) n.ref_leaf = ti;
+    else {
+        n.left = median_upper(s, s.tree[ti].left, nodes);
+        n.right = median_upper(s, s.tree[ti].right, nodes);
     }
-    const int first = (int)s.dwide.size();
-    if (first + n >= (1 << 30)) throw std::runtime_error("too many BVH nodes");
-    s.dwide.resize((size_t)first + n);
-    uint32_t meta = 0;
-    for (int k = 0; k < n; ++k) {
-        set_child_box(w, k, s.tree[slots[k]].box);
-        meta |= 1u << k;
-        if (s.tree[slots[k]].left < 0) meta |= 16u << k;
+    nodes[me] = n;
+    return me;
+}
+
+// A reference leaf's wide node: children = its primitives (consecutive sorted positions) with culling boxes.
+DWide leaf_wide(const HostScene& s, const TreeNode& t, double scene_g) {
+    DWide w = empty_wide();
+    uint32_t meta = WIDE_LEAF;
+    float qmax = 0.0f;
+    for (int k = 0; k < t.count; ++k) {
+        const HostPrim& p = s.prims[s.order[t.first + k]];
+        Box cb;
+        double pad = 0.0;
+        float q = 0.0f;
+        if (cull_pad(p, scene_g, pad, q)) {
+            for (int a = 0; a < 3; ++a) {
+                cb.lo[a] = std::nextafter((float)((double)p.box.lo[a] - pad), -FLT_MAX);
+                cb.hi[a] = std::nextafter((float)((double)p.box.hi[a] + pad), FLT_MAX);
+            }
+        } else {
+            for (int a = 0; a < 3; ++a) { cb.lo[a] = -1e30f; cb.hi[a] = 1e30f; }
+            q = 0.0f;
+        }
+        set_child_box(w, k, cb);
+        meta |= (1u << k) | ((uint32_t)p.type << (16 + 2 * k));
+        qmax = std::max(qmax, q);
     }
-    w.f[24] = bits_f((uint32_t)first);
+    w.f[24] = bits_f((uint32_t)t.first);
     w.f[25] = bits_f(meta);
-    s.dwide[me] = w;
-    for (int k = 0; k < n; ++k) emit_wide(s, slots[k], first + k, level + 1, scene_g);
+    w.f[26] = qmax;
+    return w;
+}
+
+// Collapses the binary upper tree to 4 children per node and writes the wide nodes breadth-first.
+// `me` = wide index already allocated for upper node `root`.
+void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root, double scene_g, bool by_area) {
+    struct Item { int up, wide, level, sp; };
+    std::vector<Item> queue;
+    queue.push_back({root, 0, 1, 0});
+    s.dwide.resize(1);
+    s.stack_need = 1;
+    for (size_t qi = 0; qi < queue.size(); ++qi) {
+        const Item it = queue[qi];
+        s.wide_depth = std::max(s.wide_depth, it.level);
+        const UpNode& u = up[it.up];
+        if (u.left < 0) {
+            s.dwide[it.wide] = leaf_wide(s, s.tree[u.ref_leaf], scene_g);
+            continue;
+        }
+        int slots[4], n = 0;
+        if (!by_area) {  // every other level of the binary tree: the grandchildren, in order
+            for (int child : {u.left, u.right}) {
+                if (up[child].left >= 0) { slots[n++] = up[child].left; slots[n++] = up[child].right; }
+                else slots[n++] = child;
+            }
+        } else {
+            slots[n++] = u.left;
+            slots[n++] = u.right;
+        }
+        while (by_area && n < 4) {  // open the inner child with the largest surface area
+            int pick = -1;
+            double area = -1.0;
+            for (int k = 0; k < n; ++k)
+                if (up[slots[k]].left >= 0 && half_area(up[slots[k]].box) > area) { area = half_area(up[slots[k]].box); pick = k; }
+            if (pick < 0) break;
+            const int c = slots[pick];
+            slots[pick] = up[c].left;
+            slots[n++] = up[c].right;
+        }
+        const int first = (int)s.dwide.size();
+        if (first + n >= (1 << 30)) throw std::runtime_error("too many BVH nodes");
+        s.dwide.resize((size_t)first + n);
+        DWide w = empty_wide();
+        uint32_t meta = 0;
+        for (int k = 0; k < n; ++k) {
+            set_child_box(w, k, up[slots[k]].box);
+            meta |= 1u << k;
+            if (up[slots[k]].left < 0) meta |= 16u << k;
+        }
+        w.f[24] = bits_f((uint32_t)first);
+        w.f[25] = bits_f(meta);
+        s.dwide[it.wide] = w;
+        // the traversal pushes up to n - 1 siblings before it descends: the stack a ray can need below this node
+        s.stack_need = std::max(s.stack_need, it.sp + n - 1 + 1);
+        for (int k = 0; k < n; ++k) queue.push_back({slots[k], first + k, it.level + 1, it.sp + n - 1});
+    }
 }
 
 }  // namespace
@@ -310,19 +482,33 @@ void flatten_scene(HostScene& s) {
                 g += std::max(std::fabs((double)s.tree[0].box.lo[a]), std::fabs((double)s.tree[0].box.hi[a]));
             if (g < 1e30) scene_g = std::max(scene_g, g);
         }
-        if (s.tree[0].left < 0) {
+        const char* tree_env = std::getenv("RT_B200_TREE");
+        const bool median_tree = tree_env && std::string(tree_env) == "median";
+        std::vector<UpNode> up;
+        int root = 0;
+        if (median_tree) {
+            up.reserve(s.tree.size());
+            root = median_upper(s, 0, up);
+        } else {
+            SahBuilder b{s, {}, {}, {}};
+            for (int ti = 0; ti < (int)s.tree.size(); ++ti) if (s.tree[ti].left < 0) b.leaves.push_back(ti);
+            b.nodes.reserve(2 * b.leaves.size());
+            root = b.build(0, (int)b.leaves.size(), 4);
+            up.swap(b.nodes);
+        }
+        if (up[root].left < 0) {
             // the whole scene is one reference leaf: a synthetic root with that leaf as its only child
             s.dwide.resize(2);
-            DWide root = empty_wide();
-            set_child_box(root, 0, s.tree[0].box);
-            root.f[24] = bits_f(1u);
-            root.f[25] = bits_f(1u | 16u);
-            s.dwide[0] = root;
-            s.wide_depth = 1;
-            emit_wide(s, 0, 1, 2, scene_g);
+            DWide r = empty_wide();
+            set_child_box(r, 0, s.tree[0].box);
+            r.f[24] = bits_f(1u);
+            r.f[25] = bits_f(1u | 16u);
+            s.dwide[0] = r;
+            s.dwide[1] = leaf_wide(s, s.tree[0], scene_g);
+            s.wide_depth = 2;
+            s.stack_need = 1;
         } else {
-            s.dwide.resize(1);
-            emit_wide(s, 0, 0, 1, scene_g);
+            emit_wide_tree(s, up, root, scene_g, !median_tree);
         }
     }
 

@@ -287,6 +287,14 @@ RT_DEV void wave_loop(const BvhView& bvh, Src& src, unsigned int* counter, unsig
     s.sp0 = (unsigned int)__cvta_generic_to_shared(rt_stack_smem + threadIdx.x * words);
     s.sp = s.sp0;
     s.sp_end = s.sp0 + (unsigned int)bvh.stack_depth * stride;
+#if RT_STAGE_TOP > 0
+    {   // the top of the tree, once per block, behind the stacks
+        float4* staged = reinterpret_cast<float4*>(rt_stack_smem + (size_t)bvh.stack_depth * blockDim.x * words);
+        for (int i = threadIdx.x; i < bvh.n_staged * 8; i += blockDim.x) staged[i] = __ldg(reinterpret_cast<const float4*>(bvh.wide) + i);
+        s.staged = (unsigned int)__cvta_generic_to_shared(staged);
+        __syncthreads();
+    }
+#endif
     long long item = -1;
     unsigned int pool_lo = 0, pool_hi = 0;
     bool more = true;
@@ -316,8 +324,10 @@ RT_DEV void wave_loop(const BvhView& bvh, Src& src, unsigned int* counter, unsig
         if (do_prims) trav_prims<ANY, STATS>(bvh, s, st);
         else if (can_step) {
 #pragma unroll 1
-            for (int k = 0; k < RT_STEPS_PER_VOTE && s.pend == 0u && s.cur != RT_CUR_NONE; ++k)
+            for (int k = 0; k < RT_STEPS_PER_VOTE && s.pend == 0u && s.cur != RT_CUR_NONE; ++k) {
+                if (s.sp + 3u * stride > s.sp_end) { trav_overflow<ANY>(bvh, s, st); break; }  // rare: the short stack is full
                 trav_step<ANY, STATS>(bvh, s, stride, st);
+            }
         }
         if (item >= 0 && s.pend == 0u && s.cur == RT_CUR_NONE) { src.store(item, s); item = -1; }
     }
@@ -342,7 +352,7 @@ RT_DEV void packet_loop(const BvhView& bvh, Src& src, unsigned int* counter, uns
     const unsigned int FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     // per-warp stack of 16-byte entries (node, lane mask, key, -): one STS.128 / one broadcast LDS.128
-    const unsigned int stk0 = (unsigned int)__cvta_generic_to_shared(rt_stack_smem) + (threadIdx.x >> 5) * bvh.stack_depth * 16u;
+    const unsigned int stk0 = (unsigned int)__cvta_generic_to_shared(rt_stack_smem) + (threadIdx.x >> 5) * bvh.packet_stack_depth * 16u;
     TravState s;
     s.sp0 = 0u;
     s.imax = 0.0f;
@@ -440,7 +450,7 @@ RT_DEV void packet_loop(const BvhView& bvh, Src& src, unsigned int* counter, uns
                         if (lane == 0)
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %3};" :: "r"(sp), "r"(first + slot), "r"(bk), "r"(key[j]) : "memory");
                         sp += 16u;
-                        if (RT_CHECKS && sp > stk0 + (unsigned int)bvh.stack_depth * 16u) __trap();
+                        if (RT_CHECKS && sp > stk0 + (unsigned int)bvh.packet_stack_depth * 16u) __trap();
                     }
                 }
                 const int slot = key[0] & 3;
@@ -1069,7 +1079,9 @@ struct DeviceScene {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     int sm_count = 0;
     int trace_blocks = 1, shadow_blocks = 1;  // resident blocks per SM
-    int stack_depth = 4;
+    int stack_depth = 4;         // entries per thread of the per-ray kernels' stacks
+    int packet_stack_depth = 4;  // entries per warp of the packet kernels' stacks
+    int n_staged = 0;            // RT_STAGE_TOP builds: top nodes staged in shared memory by the per-ray kernels
     size_t stack_bytes = 0;
     bool timed = false;
     int last_launches = 0;
@@ -1230,10 +1242,19 @@ static int device_scene(HostScene& h, DeviceScene** out) {
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
         d->sm_count = prop.multiProcessorCount;
-        // traversal stack in shared memory: at most 3 pushes per inner level of the wide tree
-        d->stack_depth = std::max(4, 3 * std::max(0, h.wide_depth - 1) + 1);
+        // Traversal stacks in shared memory. A ray can need h.stack_need entries (every node of its path pushed
+        // all its other children), but almost none does: the per-ray kernels get RT_B200_STACK_CAP entries per
+        // thread (default 16) -- shared memory not spent on stacks stays L1, which the node loads live on -- and a
+        // ray that runs out finishes in the exact per-lane traversal (traverse_exact_impl, own local stack), which
+        // returns the same (t, shape). The packet kernels keep one full-depth stack per WARP.
+        static const int stack_cap = [] { const char* e = std::getenv("RT_B200_STACK_CAP"); return e ? std::max(4, std::atoi(e)) : 16; }();
+        d->packet_stack_depth = std::max(4, h.stack_need);
+        d->stack_depth = std::min(d->packet_stack_depth, stack_cap);
         d->stack_bytes = (size_t)d->stack_depth * RT_TRACE_THREADS * sizeof(int) * RT_STACK_WORDS;
-        if (d->stack_bytes > 200 * 1024) { set_error("BVH too deep for the shared-memory traversal stack"); return RT_ERR_SCENE; }
+        d->n_staged = std::min<int>(RT_STAGE_TOP, (int)h.dwide.size());
+        d->stack_bytes += (size_t)d->n_staged * sizeof(DWide);
+        if ((size_t)d->packet_stack_depth * 16 * (RT_TRACE_THREADS / 32) > 200 * 1024) { set_error("BVH too deep for the shared-memory traversal stack"); return RT_ERR_SCENE; }
+        if (h.stack_need > 64) { set_error("BVH too deep for the fallback traversal stack (64 entries)"); return RT_ERR_SCENE; }
         if (d->stack_bytes > 48 * 1024) {
             CUDA_TRY(cudaFuncSetAttribute(trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
             CUDA_TRY(cudaFuncSetAttribute(trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
@@ -1499,7 +1520,7 @@ static int enqueue_frame(const HostScene& h, DeviceScene* d, FrameParams& k, boo
     // hides each kernel's tail behind the other's start. RT_B200_OVERLAP=0 serialises everything.
     static const bool overlap_enabled = [] { const char* e = std::getenv("RT_B200_OVERLAP"); return !(e && e[0] == '0'); }();
     static const bool packet_enabled = [] { const char* e = std::getenv("RT_B200_PACKET"); return !(e && e[0] == '0'); }();
-    const size_t packet_smem = (size_t)(RT_TRACE_THREADS / 32) * d->stack_depth * 16;  // per-warp stacks only
+    const size_t packet_smem = (size_t)(RT_TRACE_THREADS / 32) * d->packet_stack_depth * 16;  // per-warp stacks only
     static const bool area_packets_enabled = [] { const char* e = std::getenv("RT_B200_AREA_PACKETS"); return !(e && e[0] == '0'); }();
     const bool area_light_packets = area_packets_enabled && k.light_samples >= 8 && k.shadow_per_rec >= k.light_samples;
     const bool overlap = overlap_enabled && !serial;
@@ -1604,6 +1625,7 @@ static int render_impl(HostScene& h, const rt_render_params& rp, uint8_t* rgb8, 
     if (plan_out) *plan_out = plan;
     k.packed = packed ? 1 : 0;
     k.bvh.prims = d->prims; k.bvh.wide = d->wide; k.bvh.leafbox = d->leafbox; k.bvh.stack_depth = d->stack_depth;
+    k.bvh.packet_stack_depth = d->packet_stack_depth; k.bvh.n_staged = d->n_staged;
     k.mats = d->mats; k.lights = d->lights; k.textures = d->textures; k.texels = d->texels;
     k.hit_ids = hit_ids;
 

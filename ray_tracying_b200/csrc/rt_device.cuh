@@ -286,7 +286,9 @@ struct BvhView {
     int n_prims;
     int use_bvh;
     int prune;        // 0: visit everything, exact tests only (the reference's literal traversal)
-    int stack_depth;  // entries per thread of the shared-memory traversal stack
+    int stack_depth;  // entries per thread of the shared-memory traversal stack (per-ray kernels)
+    int packet_stack_depth;  // entries per warp (packet kernels)
+    int n_staged;  // RT_STAGE_TOP builds: the first n_staged nodes (breadth-first = the top levels) are also in shared memory
 };
 
 struct TraceStats {
@@ -313,6 +315,18 @@ RT_DEV F8 ldg256(const float* p) {
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
         : "l"(p));
+    return r;
+}
+
+// RT_STAGE_TOP = K > 0 (A/B build): every block of the per-ray kernels copies the first K nodes of the tree (the
+// top levels: nodes are numbered breadth-first) into shared memory, and trav_step reads those from there.
+#ifndef RT_STAGE_TOP
+#define RT_STAGE_TOP 0
+#endif
+RT_DEV F8 lds256(unsigned int addr) {
+    F8 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "r"(addr));
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "r"(addr + 16u));
     return r;
 }
 
@@ -494,6 +508,7 @@ struct TravState {
     unsigned int sp_end;  // RT_CHECKS: address one past the last entry
     unsigned int pend; // bit k: child k of node pend_node is a primitive waiting for its test
     int pend_node;
+    unsigned int staged;  // RT_STAGE_TOP: shared-space address of the staged top nodes
 };
 
 // Sets up a ray. Returns true when the ray is already finished (empty scene, linear scan, exact
@@ -567,7 +582,17 @@ template <bool ANY, bool STATS>
 RT_DEV void trav_step(const BvhView& b, TravState& s, unsigned int stride, TraceStats& st) {
     const int node = s.cur;
     const float* w = b.wide + (size_t)node * 32;
+#if RT_STAGE_TOP > 0
+    F8 X, Y, Z, C;
+    if (node < b.n_staged) {
+        const unsigned int a = s.staged + (unsigned int)node * 128u;
+        X = lds256(a); Y = lds256(a + 32u); Z = lds256(a + 64u); C = lds256(a + 96u);
+    } else {
+        X = ldg256(w); Y = ldg256(w + 8); Z = ldg256(w + 16); C = ldg256(w + 24);
+    }
+#else
     const F8 X = ldg256(w), Y = ldg256(w + 8), Z = ldg256(w + 16), C = ldg256(w + 24);
+#endif
     if (STATS) st.nodes += 4;
     const int first = __float_as_int(C.v[0]);
     const unsigned int meta = __float_as_uint(C.v[1]);
@@ -636,6 +661,32 @@ RT_DEV void trav_step(const BvhView& b, TravState& s, unsigned int stride, Trace
     }
     s.sp = sp;
     s.cur = next;
+}
+
+// The short shared-memory stack of a per-ray kernel cannot take another node's children: the ray starts
+// over in the exact per-lane traversal (near-first, t-pruning, its own 64-entry local stack), which returns
+// the same (t, first shape among equal t) -- the result does not depend on visit order or on which
+// conservative tests were used on the way.
+// (inlined wrapper around the out-of-line traversal, which takes the ray by value: a reference parameter of a
+// real call would pin the caller's ray state in local memory)
+#ifndef RT_OVERFLOW_NOINLINE
+#define RT_OVERFLOW_NOINLINE 0
+#endif
+template <bool ANY>
+#if RT_OVERFLOW_NOINLINE
+__device__ __noinline__ void trav_overflow(const BvhView& b, TravState& s, TraceStats& st) {
+#else
+RT_DEV void trav_overflow(const BvhView& b, TravState& s, TraceStats& st) {
+#endif
+    unsigned int boxes = 0;
+    const int4 v = traverse_exact_impl<ANY, true>(b.prims, b.wide, s.r.ox, s.r.oy, s.r.oz, s.r.dx, s.r.dy, s.r.dz, s.r.time, s.max_t, &boxes);
+    s.best_prim = ANY ? (v.x ? 0 : -1) : v.y;
+    s.best_t = __int_as_float(v.z);
+    st.prims += (unsigned int)v.w;
+    st.nodes += boxes;
+    s.cur = RT_CUR_NONE;
+    s.sp = s.sp0;
+    s.pend = 0u;
 }
 
 // The warp's primitive phase: every lane with pending primitives tests them, one class of

@@ -111,7 +111,8 @@ struct HostScene {
     std::vector<DPrim> dprims;    // sorted order
     std::vector<DWide> dwide;     // dwide[0] = root (empty when there are no shapes)
     std::vector<F4> dleafbox;     // per sorted primitive: (lo.xyz, 0), (hi.xyz, 0) of the EXACT box of its reference leaf
-    int wide_depth = 0;           // levels of the wide tree (bounds the traversal stack)
+    int wide_depth = 0;           // levels of the wide tree
+    int stack_need = 1;           // traversal stack entries a ray can need (max over root->leaf paths of the pushed siblings) + 1
     std::vector<DMaterial> dmaterials;
     std::vector<DLight> dlights;
     std::vector<DTexture> dtextures;
