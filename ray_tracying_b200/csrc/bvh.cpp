@@ -20,11 +20,32 @@
 #include <mutex>
 #include <string>
 #include <stdexcept>
+#include <thread>
 
 #include "scene.hpp"
 
 namespace rtb {
 namespace {
+
+unsigned build_threads() {
+    static const unsigned n = [] {
+        const char* e = std::getenv("RT_B200_HOST_THREADS");
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        return e ? (unsigned)std::max(1, std::atoi(e)) : std::min(hw, 64u);
+    }();
+    return n;
+}
+
+// fn(begin, end) over [0, n) in contiguous chunks, one per thread.
+template <class Fn>
+void parallel_chunks(size_t n, size_t min_chunk, Fn fn) {
+    const unsigned threads = (unsigned)std::max<size_t>(1, std::min<size_t>(build_threads(), n / std::max<size_t>(1, min_chunk)));
+    if (threads <= 1) { fn((size_t)0, n); return; }
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < threads; ++t) pool.emplace_back([=] { fn(n * t / threads, n * (t + 1) / threads); });
+    fn((size_t)0, n / threads);
+    for (std::thread& th : pool) th.join();
+}
 
 struct BuildCtx {
     const std::vector<HostPrim>& prims;
@@ -51,14 +72,28 @@ int longest_axis(const Box& b) {  // shapes.cpp:46-53
 
 // Pass 1: only permutes `order` (disjoint sub-ranges are independent, so sub-trees can run on
 // other threads without changing the result).
+// The reference sorts shape POINTERS with a comparator that looks the centres up; we sort (centre, index)
+// pairs with the same comparison on the centre. std::sort's moves are a function of the comparator's
+// outcomes and of the positions only -- never of the element type -- so the indices end up in the
+// permutation the reference's sort produces (equal centres included), while the sort itself streams
+// through memory instead of chasing an index per comparison.
+struct Keyed { float key; int idx; };
+
 void sort_ranges(BuildCtx& c, int start, int end, int par_depth) {
     if (end - start <= 4) return;
     const Box b = range_box(c, start, end);
     const int axis = longest_axis(b);
     const std::vector<float>& ctr = c.centre[axis];
-    std::sort(c.order.begin() + start, c.order.begin() + end, [&ctr](int a, int b2) { return ctr[a] < ctr[b2]; });
+    if (end - start >= 64) {
+        std::vector<Keyed> tmp((size_t)(end - start));
+        for (int k = start; k < end; ++k) tmp[(size_t)(k - start)] = {ctr[c.order[k]], c.order[k]};
+        std::sort(tmp.begin(), tmp.end(), [](const Keyed& a, const Keyed& b2) { return a.key < b2.key; });
+        for (int k = start; k < end; ++k) c.order[k] = tmp[(size_t)(k - start)].idx;
+    } else {
+        std::sort(c.order.begin() + start, c.order.begin() + end, [&ctr](int a, int b2) { return ctr[a] < ctr[b2]; });
+    }
     const int mid = (start + end) / 2;
-    if (par_depth > 0 && end - start > (1 << 15)) {
+    if (par_depth > 0 && end - start > (1 << 13)) {
         auto fut = std::async(std::launch::async, [&c, start, mid, par_depth] { sort_ranges(c, start, mid, par_depth - 1); });
         sort_ranges(c, mid, end, par_depth - 1);
         fut.get();
@@ -118,7 +153,7 @@ void build_bvh(HostScene& s) {
         c.centre[a].resize(n);
         for (int i = 0; i < n; ++i) c.centre[a][i] = (s.prims[i].box.lo[a] + s.prims[i].box.hi[a]) / 2.0f;
     }
-    sort_ranges(c, 0, n, 3);
+    sort_ranges(c, 0, n, 6);  // up to 64 sub-trees in flight
     s.tree.reserve((size_t)n);
     emit_nodes(s, 0, n);
     s.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -386,6 +421,8 @@ DWide leaf_wide(const HostScene& s, const TreeNode& t, double scene_g) {
 void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root, double scene_g, bool by_area) {
     struct Item { int up, wide, level, sp; };
     std::vector<Item> queue;
+    std::vector<std::pair<int, int>> leaf_nodes;  // (wide index, reference leaf): filled in parallel at the end
+    queue.reserve(up.size());
     queue.push_back({root, 0, 1, 0});
     s.dwide.resize(1);
     s.stack_need = 1;
@@ -394,7 +431,7 @@ void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root, doubl
         s.wide_depth = std::max(s.wide_depth, it.level);
         const UpNode& u = up[it.up];
         if (u.left < 0) {
-            s.dwide[it.wide] = leaf_wide(s, s.tree[u.ref_leaf], scene_g);
+            leaf_nodes.emplace_back(it.wide, u.ref_leaf);
             continue;
         }
         int slots[4], n = 0;
@@ -434,6 +471,9 @@ void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root, doubl
         s.stack_need = std::max(s.stack_need, it.sp + n - 1 + 1);
         for (int k = 0; k < n; ++k) queue.push_back({slots[k], first + k, it.level + 1, it.sp + n - 1});
     }
+    parallel_chunks(leaf_nodes.size(), 4096, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) s.dwide[(size_t)leaf_nodes[i].first] = leaf_wide(s, s.tree[(size_t)leaf_nodes[i].second], scene_g);
+    });
 }
 
 }  // namespace
@@ -442,7 +482,8 @@ void flatten_scene(HostScene& s) {
     const int n = (int)s.prims.size();
     // primitives in sorted order
     s.dprims.assign((size_t)n, DPrim{});
-    for (int k = 0; k < n; ++k) {
+    parallel_chunks((size_t)n, 16384, [&](size_t k_lo, size_t k_hi) {
+    for (size_t k = k_lo; k < k_hi; ++k) {
         const HostPrim& p = s.prims[s.order[k]];
         DPrim& d = s.dprims[k];
         const uint32_t tag = (uint32_t)p.type | ((uint32_t)p.material << 2);
@@ -460,15 +501,19 @@ void flatten_scene(HostScene& s) {
         }
         d.q[7] = {bits_f((uint32_t)s.order[k]), 0, 0, 0};
     }
+    });
 
     s.dleafbox.assign((size_t)2 * n, F4{0, 0, 0, 0});
-    for (const TreeNode& t : s.tree) {
+    parallel_chunks(s.tree.size(), 16384, [&](size_t t_lo, size_t t_hi) {
+    for (size_t ti = t_lo; ti < t_hi; ++ti) {
+        const TreeNode& t = s.tree[ti];
         if (t.left >= 0) continue;
         for (int k = 0; k < t.count; ++k) {
             s.dleafbox[2 * (size_t)(t.first + k)] = {t.box.lo[0], t.box.lo[1], t.box.lo[2], 0.0f};
             s.dleafbox[2 * (size_t)(t.first + k) + 1] = {t.box.hi[0], t.box.hi[1], t.box.hi[2], 0.0f};
         }
     }
+    });
     s.dwide.clear();
     s.wide_depth = 0;
     if (!s.tree.empty()) {
@@ -493,7 +538,7 @@ void flatten_scene(HostScene& s) {
             SahBuilder b{s, {}, {}, {}};
             for (int ti = 0; ti < (int)s.tree.size(); ++ti) if (s.tree[ti].left < 0) b.leaves.push_back(ti);
             b.nodes.reserve(2 * b.leaves.size());
-            root = b.build(0, (int)b.leaves.size(), 4);
+            root = b.build(0, (int)b.leaves.size(), 6);
             up.swap(b.nodes);
         }
         if (up[root].left < 0) {

@@ -7,6 +7,9 @@
 #pragma once
 
 #include <cstdint>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -98,11 +101,25 @@ inline void Value::as_float3(float out[3]) const {
     for (int k = 0; k < 3; ++k) out[k] = box->arr[k].as_float();
 }
 
+// The text ranges of the elements of one array of the document that was NOT turned into Values (see
+// Parser::defer): big scene files are mostly four arrays of shapes, whose elements the loader parses
+// and converts on several threads, each element with its own small Parser.
+struct DeferredArray {
+    std::string key;
+    std::vector<std::pair<const char*, const char*>> elements;  // [begin, end) of each element's text
+};
+
 class Parser {
 public:
     Parser(const char* begin, const char* end) : p_(begin), end_(end) {}
 
+    // Members of the ROOT object with one of these keys whose value is an array are not parsed: the value
+    // becomes an empty Array and the element ranges are recorded in `out` (last duplicate key wins, like
+    // every other member).
+    void defer(std::vector<std::string> keys, std::vector<DeferredArray>* out) { defer_keys_ = std::move(keys); deferred_ = out; }
+
     Value parse_document() {
+        depth_ = 0;
         Value v = parse_value();
         skip_ws();
         if (p_ != end_) fail("trailing characters after JSON document");
@@ -110,6 +127,74 @@ public:
     }
 
 private:
+    std::vector<std::string> defer_keys_;
+    std::vector<DeferredArray>* deferred_ = nullptr;
+    int depth_ = 0;
+
+    // Skips one value without building it; the text must be well formed as far as brackets and strings go
+    // (anything else is caught when the element itself is parsed).
+    void skip_value() {
+        skip_ws();
+        if (p_ == end_) fail("unexpected end of input");
+        if (*p_ == '"') { skip_string(); return; }
+        if (*p_ != '{' && *p_ != '[') {
+            while (p_ != end_ && *p_ != ',' && *p_ != ']' && *p_ != '}' && *p_ != ' ' && *p_ != '\n' && *p_ != '\t' && *p_ != '\r') ++p_;
+            return;
+        }
+        int depth = 0;
+        while (p_ != end_) {
+#if defined(__SSE2__)
+            // 16 bytes at a time until one of " { } [ ] shows up (scene files are mostly digits and commas)
+            while (end_ - p_ >= 16) {
+                const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p_));
+                // { } differ from [ ] by bit 5 (0x20): fold them together, then two compares cover all four
+                const __m128i f = _mm_or_si128(v, _mm_set1_epi8(0x20));
+                const __m128i hit = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(f, _mm_set1_epi8('{')), _mm_cmpeq_epi8(f, _mm_set1_epi8('}'))),
+                                                 _mm_cmpeq_epi8(v, _mm_set1_epi8('"')));
+                const int mask = _mm_movemask_epi8(hit);
+                if (mask) { p_ += __builtin_ctz((unsigned)mask); break; }
+                p_ += 16;
+            }
+            if (p_ == end_) break;
+#endif
+            const char c = *p_;
+            if (c == '"') { skip_string(); continue; }
+            ++p_;
+            if (c == '{' || c == '[') ++depth;
+            else if (c == '}' || c == ']') { if (--depth == 0) return; }
+        }
+        fail("unterminated array or object");
+    }
+    void skip_string() {
+        ++p_;
+        while (p_ != end_) {
+            const char c = *p_++;
+            if (c == '"') return;
+            if (c == '\\') { if (p_ == end_) break; ++p_; }
+        }
+        fail("unterminated string");
+    }
+    void defer_array(const std::string& key) {
+        DeferredArray* d = nullptr;
+        for (DeferredArray& e : *deferred_) if (e.key == key) d = &e;
+        if (!d) { deferred_->emplace_back(); d = &deferred_->back(); d->key = key; }
+        d->elements.clear();
+        ++p_;  // '['
+        skip_ws();
+        if (p_ != end_ && *p_ == ']') { ++p_; return; }
+        while (true) {
+            skip_ws();
+            const char* b = p_;
+            skip_value();
+            d->elements.emplace_back(b, p_);
+            skip_ws();
+            if (p_ == end_) fail("unterminated array");
+            if (*p_ == ',') { ++p_; continue; }
+            if (*p_ == ']') { ++p_; break; }
+            fail("expected ',' or ']'");
+        }
+    }
+
     const char* p_;
     const char* end_;
 
@@ -247,12 +332,13 @@ private:
 
     Value parse_array() {
         ++p_;
+        ++depth_;
         Value v;
         v.kind = Value::Array;
         v.box.reset(new Value::Box());
         v.box->arr.reserve(4);  // most arrays of a scene file are 3-vectors
         skip_ws();
-        if (p_ != end_ && *p_ == ']') { ++p_; return v; }
+        if (p_ != end_ && *p_ == ']') { ++p_; --depth_; return v; }
         while (true) {
             v.box->arr.push_back(parse_value());
             skip_ws();
@@ -261,17 +347,20 @@ private:
             if (*p_ == ']') { ++p_; break; }
             fail("expected ',' or ']'");
         }
+        --depth_;
         return v;
     }
 
     Value parse_object() {
         ++p_;
+        const bool root = depth_ == 0;
+        ++depth_;
         Value v;
         v.kind = Value::Object;
         v.box.reset(new Value::Box());
         v.box->obj.reserve(8);
         skip_ws();
-        if (p_ != end_ && *p_ == '}') { ++p_; return v; }
+        if (p_ != end_ && *p_ == '}') { ++p_; --depth_; return v; }
         while (true) {
             skip_ws();
             if (p_ == end_ || *p_ != '"') fail("expected string key");
@@ -279,7 +368,22 @@ private:
             skip_ws();
             if (p_ == end_ || *p_ != ':') fail("expected ':'");
             ++p_;
-            Value child = parse_value();
+            Value child;
+            bool deferred = false;
+            if (root && deferred_) {
+                skip_ws();
+                if (p_ != end_ && *p_ == '[')
+                    for (const std::string& k : defer_keys_) if (k == key) deferred = true;
+            }
+            if (deferred) {
+                defer_array(key);
+                child.kind = Value::Array;
+                child.box.reset(new Value::Box());
+            } else {
+                if (root && deferred_)  // a later duplicate that is not an array replaces an earlier deferred one
+                    for (size_t i = 0; i < deferred_->size(); ++i) if ((*deferred_)[i].key == key) { deferred_->erase(deferred_->begin() + (long)i); break; }
+                child = parse_value();
+            }
             // nlohmann keeps the LAST duplicate key; emulate by overwriting.
             bool replaced = false;
             for (Member& m : v.box->obj)
@@ -291,12 +395,19 @@ private:
             if (*p_ == '}') { ++p_; break; }
             fail("expected ',' or '}'");
         }
+        --depth_;
         return v;
     }
 };
 
 inline Value parse(const std::string& text) {
     Parser p(text.data(), text.data() + text.size());
+    return p.parse_document();
+}
+
+// One element of a deferred array.
+inline Value parse_range(const char* begin, const char* end) {
+    Parser p(begin, end);
     return p.parse_document();
 }
 

@@ -22,7 +22,13 @@
 #include <iostream>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
 #include <unordered_map>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "json_min.hpp"
 
@@ -162,15 +168,17 @@ rt_material_desc default_material() {  // material.hpp:52-70
 
 struct MaterialTable {
     std::vector<rt_material_desc>& out;
-    std::unordered_map<std::string, int> index;
+    std::unordered_map<uint64_t, std::vector<int>> index;  // FNV-1a of the record -> ids with that hash
     explicit MaterialTable(std::vector<rt_material_desc>& o) : out(o) {}
     int intern(const rt_material_desc& m) {
-        std::string key(reinterpret_cast<const char*>(&m), sizeof(m));
-        auto it = index.find(key);
-        if (it != index.end()) return it->second;
-        int id = (int)out.size();
+        const unsigned char* b = reinterpret_cast<const unsigned char*>(&m);
+        uint64_t h = 1469598103934665603ull;
+        for (size_t i = 0; i < sizeof(m); ++i) { h ^= b[i]; h *= 1099511628211ull; }
+        std::vector<int>& ids = index[h];
+        for (int id : ids) if (std::memcmp(&out[(size_t)id], &m, sizeof(m)) == 0) return id;
+        const int id = (int)out.size();
         out.push_back(m);
-        index.emplace(std::move(key), id);
+        ids.push_back(id);
         return id;
     }
 };
@@ -199,8 +207,12 @@ struct TextureTable {
     }
 };
 
-rt_material_desc parse_material(const Value& mj, TextureTable& textures) {
+// parse_material (json_loader.cpp:30-97). The texture is returned by NAME: elements are converted on
+// several threads, and the texture table (file I/O, ids in first-use order) is filled afterwards, serially,
+// in element order. `warn` collects what the reference would have printed.
+rt_material_desc parse_material(const Value& mj, std::string& texture_file, std::string& warn) {
     rt_material_desc m = default_material();
+    texture_file.clear();
     try {
         if (const Value* v = mj.find("diffuse_color")) v->as_float3(m.diffuse_color);
         if (const Value* v = mj.find("specular_color")) v->as_float3(m.specular_color);
@@ -216,10 +228,11 @@ rt_material_desc parse_material(const Value& mj, TextureTable& textures) {
         m.transparency = mj.value_float("transparency", 0.0f);
         m.refractive_index = mj.value_float("refractive_index", 1.0f);
         if (const Value* tf = mj.find("texture_file")) {
-            if (tf->is_string() && !tf->str().empty()) m.texture = textures.load(tf->str());
+            if (tf->is_string() && !tf->str().empty()) texture_file = tf->str();
         }
     } catch (const std::exception& e) {
-        std::cerr << "Warning: Error parsing material data: " << e.what() << std::endl;
+        warn += std::string("Warning: Error parsing material data: ") + e.what() + "\n";
+        texture_file.clear();
         return default_material();
     }
     return m;
@@ -270,89 +283,128 @@ void load_lights(const Value& root, std::vector<rt_light_desc>& lights) {
     if (lights.empty()) std::cerr << "Warning: No valid lights were loaded." << std::endl;
 }
 
-void load_shapes(const Value& root, HostScene& s, MaterialTable& mats, TextureTable& textures) {
-    const float zero3[3] = {0, 0, 0};
-    auto material_of = [&](const Value& j) {
-        rt_material_desc m = default_material();
-        if (const Value* mj = j.find("material")) m = parse_material(*mj, textures);
-        return mats.intern(m);
+// One element of "spheres" / "cubes" / "rectangles" / "planes" after conversion (json_loader.cpp:180-332).
+struct ShapeOut {
+    bool ok = false;
+    HostPrim prim;             // material = -1 until the serial pass interns `mat`
+    rt_material_desc mat;
+    std::string texture_file;  // resolved in the serial pass
+    std::string warn;          // what the reference would have printed for this element
+};
+
+void convert_shape(int type, const Value& j, ShapeOut& o) {
+    static const float zero3[3] = {0, 0, 0};
+    o.ok = false;
+    if (!j.is_object()) return;
+    auto material_of = [&](const Value& e) {
+        o.mat = default_material();
+        o.texture_file.clear();
+        if (const Value* mj = e.find("material")) o.mat = parse_material(*mj, o.texture_file, o.warn);
     };
-    // 1. spheres (json_loader.cpp:180-234)
-    if (const Value* arr = root.find("spheres"); arr && arr->is_array()) {
-        for (const Value& j : arr->array()) {
-            if (!j.is_object()) continue;
-            try {
-                float t[3], r[3] = {0, 0, 0}, sc[3] = {1, 1, 1}, vel[3] = {0, 0, 0};
-                j.at("location").as_float3(t);
-                if (const Value* v = j.find("rotation")) v->as_float3(r);
-                const Value* sv = j.find("scale");
-                if (sv && sv->is_array()) sv->as_float3(sc);
-                else if (const Value* rv = j.find("radius")) { float rad = rv->as_float(); sc[0] = sc[1] = sc[2] = rad; }
-                int mat = material_of(j);
-                if (const Value* v = j.find("velocity")) v->as_float3(vel);
-                vel[0] = vel[0] / 5; vel[1] = vel[1] / 5; vel[2] = vel[2] / 5;
-                s.prims.push_back(make_prim(RT_SPHERE, mat, t, r, sc, vel, nullptr));
-            } catch (const std::exception& e) {
-                std::cerr << "Warning: Error parsing sphere: " << e.what() << std::endl;
+    try {
+        if (type == RT_SPHERE) {  // json_loader.cpp:180-234
+            float t[3], r[3] = {0, 0, 0}, sc[3] = {1, 1, 1}, vel[3] = {0, 0, 0};
+            j.at("location").as_float3(t);
+            if (const Value* v = j.find("rotation")) v->as_float3(r);
+            const Value* sv = j.find("scale");
+            if (sv && sv->is_array()) sv->as_float3(sc);
+            else if (const Value* rv = j.find("radius")) { float rad = rv->as_float(); sc[0] = sc[1] = sc[2] = rad; }
+            material_of(j);
+            if (const Value* v = j.find("velocity")) v->as_float3(vel);
+            vel[0] = vel[0] / 5; vel[1] = vel[1] / 5; vel[2] = vel[2] / 5;
+            o.prim = make_prim(RT_SPHERE, -1, t, r, sc, vel, nullptr);
+        } else if (type == RT_CUBE) {  // json_loader.cpp:237-278
+            if (!j.contains("translation") || !j.contains("rotation")) {
+                o.warn += "Warning: Skipping invalid cube definition.\n";
+                return;
             }
+            float t[3], r[3], sc[3] = {1, 1, 1};
+            j.at("translation").as_float3(t);
+            j.at("rotation").as_float3(r);
+            if (const Value* sv = j.find("scale")) {
+                if (sv->is_array()) sv->as_float3(sc);
+                else if (sv->is_number()) { float v = sv->as_float(); sc[0] = sc[1] = sc[2] = v; }
+            }
+            material_of(j);
+            o.prim = make_prim(RT_CUBE, -1, t, r, sc, zero3, nullptr);
+        } else if (type == RT_RECTANGLE) {  // json_loader.cpp:282-301
+            float t[3], r[3], sc[3];
+            j.at("translation").as_float3(t);
+            j.at("rotation").as_float3(r);
+            j.at("scale").as_float3(sc);
+            material_of(j);
+            o.prim = make_prim(RT_RECTANGLE, -1, t, r, sc, zero3, nullptr);
+        } else {  // planes, json_loader.cpp:304-332
+            const Value* cj = j.find("corners");
+            if (!cj || !cj->is_array() || cj->array().size() != 4) {
+                o.warn += "Warning: Skipping invalid plane definition.\n";
+                return;
+            }
+            float corners[12];
+            for (int k = 0; k < 4; ++k) cj->array()[k].as_float3(corners + 3 * k);
+            material_of(j);
+            o.prim = make_prim(RT_PLANE, -1, zero3, zero3, zero3, zero3, corners);
         }
+        o.ok = true;
+    } catch (const std::exception& e) {
+        static const char* what[4] = {"Warning: Error parsing sphere: ", "Warning: Error parsing cube entry: ",
+                                      "Warning: Error parsing rectangle: ", "Warning: Error parsing plane entry: "};
+        o.warn += std::string(what[type]) + e.what() + "\n";
     }
-    // 2. cubes (json_loader.cpp:237-278)
-    if (const Value* arr = root.find("cubes"); arr && arr->is_array()) {
-        for (const Value& j : arr->array()) {
-            if (!j.is_object()) continue;
-            try {
-                if (!j.contains("translation") || !j.contains("rotation")) {
-                    std::cerr << "Warning: Skipping invalid cube definition." << std::endl;
-                    continue;
+}
+
+unsigned host_threads() {
+    static const unsigned n = [] {
+        const char* e = std::getenv("RT_B200_HOST_THREADS");
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        return e ? (unsigned)std::max(1, std::atoi(e)) : std::min(hw, 64u);
+    }();
+    return n;
+}
+
+// The four shape arrays, in the loader's push order (spheres, cubes, rectangles, planes). Their elements
+// were left as text ranges by the document parse (jsonmin::DeferredArray): here every element is parsed and
+// converted on its own, chunks of elements on different threads; interning of materials and loading of
+// textures -- whose ids depend on first-use order -- and the warnings follow serially in element order, so
+// the scene is the one a serial loader builds.
+void load_shapes(const std::vector<jsonmin::DeferredArray>& arrays, HostScene& s, MaterialTable& mats, TextureTable& textures) {
+    static const char* keys[4] = {"spheres", "cubes", "rectangles", "planes"};
+    static const int types[4] = {RT_SPHERE, RT_CUBE, RT_RECTANGLE, RT_PLANE};
+    size_t total = 0;
+    for (const jsonmin::DeferredArray& a : arrays) total += a.elements.size();
+    s.prims.reserve(total);
+    for (int c = 0; c < 4; ++c) {
+        const jsonmin::DeferredArray* arr = nullptr;
+        for (const jsonmin::DeferredArray& a : arrays) if (a.key == keys[c]) arr = &a;
+        if (!arr || arr->elements.empty()) continue;
+        const size_t n = arr->elements.size();
+        std::vector<ShapeOut> out(n);
+        const unsigned threads = (unsigned)std::max<size_t>(1, std::min<size_t>(host_threads(), n / 2048 + 1));
+        std::vector<std::string> fatal(threads);
+        auto work = [&](unsigned t) {
+            const size_t lo = n * t / threads, hi = n * (t + 1) / threads;
+            for (size_t i = lo; i < hi; ++i) {
+                Value j;
+                try {
+                    j = jsonmin::parse_range(arr->elements[i].first, arr->elements[i].second);
+                } catch (const std::exception& e) {  // malformed JSON: the whole document is rejected, like the reference's parse
+                    if (fatal[t].empty()) fatal[t] = e.what();
+                    return;
                 }
-                float t[3], r[3], sc[3] = {1, 1, 1};
-                j.at("translation").as_float3(t);
-                j.at("rotation").as_float3(r);
-                if (const Value* sv = j.find("scale")) {
-                    if (sv->is_array()) sv->as_float3(sc);
-                    else if (sv->is_number()) { float v = sv->as_float(); sc[0] = sc[1] = sc[2] = v; }
-                }
-                int mat = material_of(j);
-                s.prims.push_back(make_prim(RT_CUBE, mat, t, r, sc, zero3, nullptr));
-            } catch (const std::exception& e) {
-                std::cerr << "Warning: Error parsing cube entry: " << e.what() << std::endl;
+                convert_shape(types[c], j, out[i]);
             }
-        }
-    }
-    // 3. rectangles (json_loader.cpp:282-301)
-    if (const Value* arr = root.find("rectangles"); arr && arr->is_array()) {
-        for (const Value& j : arr->array()) {
-            if (!j.is_object()) continue;
-            try {
-                float t[3], r[3], sc[3];
-                j.at("translation").as_float3(t);
-                j.at("rotation").as_float3(r);
-                j.at("scale").as_float3(sc);
-                int mat = material_of(j);
-                s.prims.push_back(make_prim(RT_RECTANGLE, mat, t, r, sc, zero3, nullptr));
-            } catch (const std::exception& e) {
-                std::cerr << "Warning: Error parsing rectangle: " << e.what() << std::endl;
-            }
-        }
-    }
-    // 4. planes (json_loader.cpp:304-332)
-    if (const Value* arr = root.find("planes"); arr && arr->is_array()) {
-        for (const Value& j : arr->array()) {
-            if (!j.is_object()) continue;
-            try {
-                const Value* cj = j.find("corners");
-                if (!cj || !cj->is_array() || cj->array().size() != 4) {
-                    std::cerr << "Warning: Skipping invalid plane definition." << std::endl;
-                    continue;
-                }
-                float corners[12];
-                for (int k = 0; k < 4; ++k) cj->array()[k].as_float3(corners + 3 * k);
-                int mat = material_of(j);
-                s.prims.push_back(make_prim(RT_PLANE, mat, zero3, zero3, zero3, zero3, corners));
-            } catch (const std::exception& e) {
-                std::cerr << "Warning: Error parsing plane entry: " << e.what() << std::endl;
-            }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < threads; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (std::thread& th : pool) th.join();
+        for (const std::string& f : fatal) if (!f.empty()) throw std::runtime_error(f);
+        for (ShapeOut& o : out) {
+            if (!o.warn.empty()) std::cerr << o.warn << std::flush;
+            if (!o.ok) continue;
+            if (!o.texture_file.empty()) o.mat.texture = textures.load(o.texture_file);
+            o.prim.material = mats.intern(o.mat);
+            s.prims.push_back(o.prim);
         }
     }
     if (s.prims.empty()) std::cerr << "Warning: No valid shapes were loaded." << std::endl;
@@ -390,27 +442,41 @@ void load_scene_json(const std::string& path, const std::string& texture_dir, Ho
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     const auto t0 = now();
-    std::string text;
+    // the file is mapped, not copied: the shape elements are parsed straight out of the page cache
+    struct Mapping {
+        const char* data = nullptr;
+        size_t size = 0;
+        int fd = -1;
+        ~Mapping() {
+            if (data && size) ::munmap(const_cast<char*>(data), size);
+            if (fd >= 0) ::close(fd);
+        }
+    } text;
     {
-        std::FILE* f = std::fopen(path.c_str(), "rb");
-        if (!f) throw std::runtime_error("Could not open JSON file: " + path);
-        std::fseek(f, 0, SEEK_END);
-        const long size = std::ftell(f);
-        std::fseek(f, 0, SEEK_SET);
-        text.resize(size > 0 ? (size_t)size : 0);
-        const size_t got = text.empty() ? 0 : std::fread(&text[0], 1, text.size(), f);
-        std::fclose(f);
-        text.resize(got);
+        text.fd = ::open(path.c_str(), O_RDONLY);
+        if (text.fd < 0) throw std::runtime_error("Could not open JSON file: " + path);
+        struct stat st;
+        if (::fstat(text.fd, &st) != 0 || !S_ISREG(st.st_mode)) throw std::runtime_error("Could not open JSON file: " + path);
+        text.size = (size_t)st.st_size;
+        if (text.size > 0) {
+            void* m = ::mmap(nullptr, text.size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, text.fd, 0);
+            if (m == MAP_FAILED) throw std::runtime_error("Could not map JSON file: " + path);
+            text.data = static_cast<const char*>(m);
+        }
     }
     const auto t1 = now();
-    Value root = jsonmin::parse(text);
+    // the document without the elements of the four shape arrays (those stay text ranges into `text`)
+    std::vector<jsonmin::DeferredArray> shape_arrays;
+    jsonmin::Parser parser(text.data, text.data + text.size);
+    parser.defer({"spheres", "cubes", "rectangles", "planes"}, &shape_arrays);
+    Value root = parser.parse_document();
     const auto t2 = now();
     if (!root.is_object()) throw std::runtime_error("scene root must be a JSON object");
     load_camera(root, s.cam);
     load_lights(root, s.lights);
     MaterialTable mats(s.materials);
     TextureTable textures{s, texture_dir.empty() ? std::string("../../Textures") : texture_dir, {}};
-    load_shapes(root, s, mats, textures);
+    load_shapes(shape_arrays, s, mats, textures);
     const auto t3 = now();
     finalize_scene(s);
     if (timing)
