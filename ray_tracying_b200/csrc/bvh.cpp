@@ -12,6 +12,8 @@
 // rounding is monotonic, so they pass too). Which <=4 shapes share a leaf box therefore decides
 // which shapes are tested at all, and hit IDs are only bit-exact with identical leaves.
 #include <algorithm>
+#include <atomic>
+#include <cstdio>
 #include <cfloat>
 #include <cmath>
 #include <chrono>
@@ -247,21 +249,29 @@ void set_child_box(DWide& w, int c, const Box& b) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// The device tree. Its LEAVES are the reference's leaves (<= 4 shapes each, acceleration.cpp:29-33):
-// a shape may only be tested if the exact box of its reference leaf passes AABB::intersect, so the
-// leaf partition and the leaf boxes are the reference's. Everything ABOVE the
-// leaves is ours -- the result (min t, first shape among equal t) does not depend on how the leaves
-// are grouped -- so the upper levels are built for traversal cost:
-//   RT_B200_TREE=sah (default): binary tree over the leaves by binned surface-area heuristic
-//       (16 bins per axis on the leaf-box centroids, cost = SA_left * n_left + SA_right * n_right),
-//       collapsed to 4 children per node by repeatedly opening the child with the largest area;
-//   RT_B200_TREE=median: the reference's own median-split tree with every other level skipped.
-// Nodes are numbered breadth-first, the children of a node consecutively (index = first + slot).
+// The device tree: a 4-wide BVH over the PRIMITIVES, built for traversal cost.
+//
+// What the reference prescribes is only this: a shape is tested iff the EXACT box of
+// its reference leaf passes AABB::intersect, and the answer is (min t, first shape in shape_list order among
+// equal t). That condition is carried per primitive -- the "gate": HostScene::dleafbox holds the leaf box of
+// every primitive, and the traversal evaluates the reference's test on it before it runs the primitive's
+// intersection routine. Everything else is ours: the boxes of this tree are CULLING boxes (cull_pad: they
+// contain every ray for which the primitive's routine could report a hit) and their unions, used only to skip
+// work, so the tree may group primitives in any way:
+//   * binary tree by binned surface-area heuristic (16 bins per axis on the culling-box centroids, cost =
+//     SA_left * n_left + SA_right * n_right) down to single primitives,
+//   * collapsed to <= 4 children per node by repeatedly opening the inner child with the largest area; a node's
+//     children are inner nodes (slots 0..ni-1, consecutive node indices first + slot) and primitives (the
+//     following slots, sorted positions in f[27..30]),
+//   * nodes numbered breadth-first.
+// Compared with a tree whose leaves are the reference's leaves (round-2 first version, tag r2-sah-leaves) a ray
+// visits about a third fewer nodes: the level of "leaf nodes" (4 culling boxes behind every leaf box) is gone.
 // ---------------------------------------------------------------------------------------------
 struct UpNode {
     Box box;
+    float q = 0.0f;             // largest sphere cull coefficient below
     int left = -1, right = -1;  // UpNode indices; -1 for a leaf
-    int ref_leaf = -1;          // index into HostScene::tree of the reference leaf (leaves only)
+    int prim = -1;              // sorted position of the primitive (leaves only)
 };
 
 inline double half_area(const Box& b) {
@@ -274,44 +284,39 @@ inline void box_merge(Box& b, const Box& o) {
 }
 
 struct SahBuilder {
-    const HostScene& s;
-    std::vector<int> leaves;      // reference leaf (tree index) per position, permuted in place
-    std::vector<UpNode> nodes;
-    std::mutex mu;                // guards `nodes` growth when sub-trees are built on other threads
+    const std::vector<Box>& cull;   // culling box per sorted position
+    const std::vector<float>& cq;   // sphere coefficient per sorted position
+    double min_frac;                // a split must leave at least this share of the primitives on each side
+    std::vector<int> items;         // sorted positions, permuted in place
+    std::vector<UpNode> nodes;      // pre-sized to 2n - 1: sub-trees built on other threads claim slots with `next`
+    std::atomic<int> next{0};
 
-    int alloc() {
-        std::lock_guard<std::mutex> lock(mu);
-        nodes.emplace_back();
-        return (int)nodes.size() - 1;
-    }
-    void set(int id, const UpNode& n) {
-        std::lock_guard<std::mutex> lock(mu);
-        nodes[id] = n;
-    }
+    int alloc() { return next.fetch_add(1, std::memory_order_relaxed); }
+    void set(int id, const UpNode& n) { nodes[(size_t)id] = n; }
 
-    // builds the sub-tree over leaves[lo, hi) and returns its node id
+    // builds the sub-tree over items[lo, hi) and returns its node id
     int build(int lo, int hi, int par_depth) {
         const int me = alloc();
         UpNode n;
         box_reset(n.box);
-        for (int k = lo; k < hi; ++k) box_merge(n.box, s.tree[leaves[k]].box);
+        for (int k = lo; k < hi; ++k) { box_merge(n.box, cull[(size_t)items[k]]); n.q = std::max(n.q, cq[(size_t)items[k]]); }
         if (hi - lo == 1) {
-            n.ref_leaf = leaves[lo];
+            n.prim = items[lo];
             set(me, n);
             return me;
         }
-        // binned SAH over the centroids of the leaf boxes
         constexpr int NB = 16;
         Box cb;
         box_reset(cb);
         for (int k = lo; k < hi; ++k) {
-            const Box& b = s.tree[leaves[k]].box;
+            const Box& b = cull[(size_t)items[k]];
             for (int a = 0; a < 3; ++a) {
                 const float c = 0.5f * (b.lo[a] + b.hi[a]);
                 cb.lo[a] = std::min(cb.lo[a], c);
                 cb.hi[a] = std::max(cb.hi[a], c);
             }
         }
+        const int min_side = std::max(1, (int)(min_frac * (hi - lo)));
         int best_axis = -1, best_bin = -1;
         double best_cost = 1e300;
         for (int a = 0; a < 3; ++a) {
@@ -322,7 +327,7 @@ struct SahBuilder {
             for (int b = 0; b < NB; ++b) { box_reset(bins[b]); cnt[b] = 0; }
             const float scale = (float)NB / ext;
             for (int k = lo; k < hi; ++k) {
-                const Box& b = s.tree[leaves[k]].box;
+                const Box& b = cull[(size_t)items[k]];
                 const int bi = std::min(NB - 1, std::max(0, (int)((0.5f * (b.lo[a] + b.hi[a]) - cb.lo[a]) * scale)));
                 box_merge(bins[bi], b);
                 cnt[bi]++;
@@ -343,22 +348,32 @@ struct SahBuilder {
             for (int b = 0; b + 1 < NB; ++b) {
                 if (cnt[b]) box_merge(acc, bins[b]);
                 c += cnt[b];
-                if (c == 0 || right_cnt[b + 1] == 0) continue;
+                if (c < min_side || right_cnt[b + 1] < min_side) continue;
                 const double cost = half_area(acc) * c + right_area[b + 1] * right_cnt[b + 1];
                 if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b; }
             }
         }
-        int mid = (lo + hi) / 2;
+        int mid = -1;
         if (best_axis >= 0) {
             const int a = best_axis;
             const float scale = (float)NB / (cb.hi[a] - cb.lo[a]);
-            auto it = std::partition(leaves.begin() + lo, leaves.begin() + hi, [&](int t) {
-                const Box& b = s.tree[t].box;
+            auto it = std::partition(items.begin() + lo, items.begin() + hi, [&](int t) {
+                const Box& b = cull[(size_t)t];
                 return std::min(NB - 1, std::max(0, (int)((0.5f * (b.lo[a] + b.hi[a]) - cb.lo[a]) * scale))) <= best_bin;
             });
-            mid = (int)(it - leaves.begin());
+            mid = (int)(it - items.begin());
         }
-        if (mid <= lo || mid >= hi) mid = (lo + hi) / 2;  // all centroids equal: split the (position-ordered) run in half
+        if (mid <= lo || mid >= hi) {
+            // no admissible SAH split (all centroids equal, or the balance bound excludes every bin boundary):
+            // median of the centroids along the longest axis
+            int a = 0;
+            for (int i = 1; i < 3; ++i) if (cb.hi[i] - cb.lo[i] > cb.hi[a] - cb.lo[a]) a = i;
+            mid = (lo + hi) / 2;
+            std::nth_element(items.begin() + lo, items.begin() + mid, items.begin() + hi, [&](int x, int y) {
+                const float cx = cull[(size_t)x].lo[a] + cull[(size_t)x].hi[a], cy = cull[(size_t)y].lo[a] + cull[(size_t)y].hi[a];
+                return cx < cy || (cx == cy && x < y);
+            });
+        }
         if (par_depth > 0 && hi - lo > (1 << 14)) {
             auto fut = std::async(std::launch::async, [this, lo, mid, par_depth] { return build(lo, mid, par_depth - 1); });
             n.right = build(mid, hi, par_depth - 1);
@@ -372,108 +387,62 @@ struct SahBuilder {
     }
 };
 
-// The reference's own tree as an UpNode tree (RT_B200_TREE=median).
-int median_upper(const HostScene& s, int ti, std::vector<UpNode>& nodes) {
-    const int me = (int)nodes.size();
-    nodes.emplace_back();
-    UpNode n;
-    n.box = s.tree[ti].box;
-    if (s.tree[ti].left < 0) n.ref_leaf = ti;
-    else {
-        n.left = median_upper(s, s.tree[ti].left, nodes);
-        n.right = median_upper(s, s.tree[ti].right, nodes);
-    }
-    nodes[me] = n;
-    return me;
-}
-
-// A reference leaf's wide node: children = its primitives (consecutive sorted positions) with culling boxes.
-DWide leaf_wide(const HostScene& s, const TreeNode& t, double scene_g) {
-    DWide w = empty_wide();
-    uint32_t meta = WIDE_LEAF;
-    float qmax = 0.0f;
-    for (int k = 0; k < t.count; ++k) {
-        const HostPrim& p = s.prims[s.order[t.first + k]];
-        Box cb;
-        double pad = 0.0;
-        float q = 0.0f;
-        if (cull_pad(p, scene_g, pad, q)) {
-            for (int a = 0; a < 3; ++a) {
-                cb.lo[a] = std::nextafter((float)((double)p.box.lo[a] - pad), -FLT_MAX);
-                cb.hi[a] = std::nextafter((float)((double)p.box.hi[a] + pad), FLT_MAX);
-            }
-        } else {
-            for (int a = 0; a < 3; ++a) { cb.lo[a] = -1e30f; cb.hi[a] = 1e30f; }
-            q = 0.0f;
-        }
-        set_child_box(w, k, cb);
-        meta |= (1u << k) | ((uint32_t)p.type << (16 + 2 * k));
-        qmax = std::max(qmax, q);
-    }
-    w.f[24] = bits_f((uint32_t)t.first);
-    w.f[25] = bits_f(meta);
-    w.f[26] = qmax;
-    return w;
-}
-
-// Collapses the binary upper tree to 4 children per node and writes the wide nodes breadth-first.
-// `me` = wide index already allocated for upper node `root`.
-void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root, double scene_g, bool by_area) {
+// Collapses the binary tree to <= 4 children per node and writes the wide nodes breadth-first.
+void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root) {
     struct Item { int up, wide, level, sp; };
     std::vector<Item> queue;
-    std::vector<std::pair<int, int>> leaf_nodes;  // (wide index, reference leaf): filled in parallel at the end
-    queue.reserve(up.size());
+    queue.reserve(up.size() / 2 + 2);
     queue.push_back({root, 0, 1, 0});
-    s.dwide.resize(1);
+    s.dwide.assign(1, empty_wide());
     s.stack_need = 1;
+    s.wide_depth = 0;
     for (size_t qi = 0; qi < queue.size(); ++qi) {
         const Item it = queue[qi];
         s.wide_depth = std::max(s.wide_depth, it.level);
-        const UpNode& u = up[it.up];
-        if (u.left < 0) {
-            leaf_nodes.emplace_back(it.wide, u.ref_leaf);
-            continue;
-        }
+        const UpNode& u = up[(size_t)it.up];
         int slots[4], n = 0;
-        if (!by_area) {  // every other level of the binary tree: the grandchildren, in order
-            for (int child : {u.left, u.right}) {
-                if (up[child].left >= 0) { slots[n++] = up[child].left; slots[n++] = up[child].right; }
-                else slots[n++] = child;
-            }
-        } else {
+        if (u.left < 0) slots[n++] = it.up;  // a scene of one primitive: the root holds it
+        else {
             slots[n++] = u.left;
             slots[n++] = u.right;
         }
-        while (by_area && n < 4) {  // open the inner child with the largest surface area
+        while (n < 4) {  // open the inner child with the largest surface area
             int pick = -1;
             double area = -1.0;
             for (int k = 0; k < n; ++k)
-                if (up[slots[k]].left >= 0 && half_area(up[slots[k]].box) > area) { area = half_area(up[slots[k]].box); pick = k; }
+                if (up[(size_t)slots[k]].left >= 0 && half_area(up[(size_t)slots[k]].box) > area) { area = half_area(up[(size_t)slots[k]].box); pick = k; }
             if (pick < 0) break;
             const int c = slots[pick];
-            slots[pick] = up[c].left;
-            slots[n++] = up[c].right;
+            slots[pick] = up[(size_t)c].left;
+            slots[n++] = up[(size_t)c].right;
         }
+        // inner children first (consecutive node indices), primitives behind them
+        std::stable_partition(slots, slots + n, [&](int c) { return up[(size_t)c].left >= 0; });
+        int ni = 0;
+        while (ni < n && up[(size_t)slots[ni]].left >= 0) ++ni;
         const int first = (int)s.dwide.size();
-        if (first + n >= (1 << 30)) throw std::runtime_error("too many BVH nodes");
-        s.dwide.resize((size_t)first + n);
+        if (first + ni >= (1 << 30)) throw std::runtime_error("too many BVH nodes");
+        s.dwide.resize((size_t)first + ni, empty_wide());
         DWide w = empty_wide();
         uint32_t meta = 0;
         for (int k = 0; k < n; ++k) {
-            set_child_box(w, k, up[slots[k]].box);
+            const UpNode& c = up[(size_t)slots[k]];
+            set_child_box(w, k, c.box);
             meta |= 1u << k;
-            if (up[slots[k]].left < 0) meta |= 16u << k;
+            if (c.left < 0) {
+                const HostPrim& p = s.prims[(size_t)s.order[(size_t)c.prim]];
+                meta |= (16u << k) | ((uint32_t)p.type << (16 + 2 * k));
+                w.f[27 + k] = bits_f((uint32_t)c.prim);
+            }
         }
         w.f[24] = bits_f((uint32_t)first);
         w.f[25] = bits_f(meta);
-        s.dwide[it.wide] = w;
-        // the traversal pushes up to n - 1 siblings before it descends: the stack a ray can need below this node
-        s.stack_need = std::max(s.stack_need, it.sp + n - 1 + 1);
-        for (int k = 0; k < n; ++k) queue.push_back({slots[k], first + k, it.level + 1, it.sp + n - 1});
+        w.f[26] = u.q;
+        s.dwide[(size_t)it.wide] = w;
+        // the traversal pushes up to ni - 1 sibling nodes before it descends: the stack a ray can need below here
+        s.stack_need = std::max(s.stack_need, it.sp + std::max(0, ni - 1) + 1);
+        for (int k = 0; k < ni; ++k) queue.push_back({slots[k], first + k, it.level + 1, it.sp + std::max(0, ni - 1)});
     }
-    parallel_chunks(leaf_nodes.size(), 4096, [&](size_t lo, size_t hi) {
-        for (size_t i = lo; i < hi; ++i) s.dwide[(size_t)leaf_nodes[i].first] = leaf_wide(s, s.tree[(size_t)leaf_nodes[i].second], scene_g);
-    });
 }
 
 }  // namespace
@@ -516,8 +485,8 @@ void flatten_scene(HostScene& s) {
     });
     s.dwide.clear();
     s.wide_depth = 0;
+    s.stack_need = 1;
     if (!s.tree.empty()) {
-        s.dwide.reserve(s.tree.size() / 2 + 2);
         // bound of |x|+|y|+|z| over every ray origin: the scene box and the camera (+ lens radius)
         double scene_g = std::fabs((double)s.cam.location[0]) + std::fabs((double)s.cam.location[1]) +
                          std::fabs((double)s.cam.location[2]) + 2.0 * std::fabs((double)s.cam.aperture);
@@ -527,33 +496,47 @@ void flatten_scene(HostScene& s) {
                 g += std::max(std::fabs((double)s.tree[0].box.lo[a]), std::fabs((double)s.tree[0].box.hi[a]));
             if (g < 1e30) scene_g = std::max(scene_g, g);
         }
-        const char* tree_env = std::getenv("RT_B200_TREE");
-        const bool median_tree = tree_env && std::string(tree_env) == "median";
-        std::vector<UpNode> up;
-        int root = 0;
-        if (median_tree) {
-            up.reserve(s.tree.size());
-            root = median_upper(s, 0, up);
-        } else {
-            SahBuilder b{s, {}, {}, {}};
-            for (int ti = 0; ti < (int)s.tree.size(); ++ti) if (s.tree[ti].left < 0) b.leaves.push_back(ti);
-            b.nodes.reserve(2 * b.leaves.size());
-            root = b.build(0, (int)b.leaves.size(), 6);
-            up.swap(b.nodes);
-        }
-        if (up[root].left < 0) {
-            // the whole scene is one reference leaf: a synthetic root with that leaf as its only child
-            s.dwide.resize(2);
-            DWide r = empty_wide();
-            set_child_box(r, 0, s.tree[0].box);
-            r.f[24] = bits_f(1u);
-            r.f[25] = bits_f(1u | 16u);
-            s.dwide[0] = r;
-            s.dwide[1] = leaf_wide(s, s.tree[0], scene_g);
-            s.wide_depth = 2;
-            s.stack_need = 1;
-        } else {
-            emit_wide_tree(s, up, root, scene_g, !median_tree);
+        // culling box + sphere coefficient of every primitive (sorted order). A primitive whose culling box
+        // cannot be bounded (degenerate quads, cull_pad) takes the box of its reference leaf instead: it is only
+        // ever tested when that box passes.
+        std::vector<Box> cull((size_t)n);
+        std::vector<float> cq((size_t)n, 0.0f);
+        parallel_chunks((size_t)n, 8192, [&](size_t k_lo, size_t k_hi) {
+            for (size_t k = k_lo; k < k_hi; ++k) {
+                const HostPrim& p = s.prims[(size_t)s.order[k]];
+                double pad = 0.0;
+                float q = 0.0f;
+                Box cb;
+                if (cull_pad(p, scene_g, pad, q)) {
+                    for (int a = 0; a < 3; ++a) {
+                        cb.lo[a] = std::nextafter((float)((double)p.box.lo[a] - pad), -FLT_MAX);
+                        cb.hi[a] = std::nextafter((float)((double)p.box.hi[a] + pad), FLT_MAX);
+                    }
+                } else {
+                    const F4 lo = s.dleafbox[2 * k], hi = s.dleafbox[2 * k + 1];
+                    const float l3[3] = {lo.x, lo.y, lo.z}, h3[3] = {hi.x, hi.y, hi.z};
+                    for (int a = 0; a < 3; ++a) {
+                        const double m = 1e-6 * (std::fabs((double)l3[a]) + std::fabs((double)h3[a])) + 1e-6;
+                        cb.lo[a] = std::nextafter((float)((double)l3[a] - m), -FLT_MAX);
+                        cb.hi[a] = std::nextafter((float)((double)h3[a] + m), FLT_MAX);
+                    }
+                    q = 0.0f;
+                }
+                cull[k] = cb;
+                cq[k] = q;
+            }
+        });
+        // the traversal stacks live in shared memory (36 entries x 6 blocks is what an SM holds): a tree that could
+        // need more is rebuilt with a balance bound
+        for (double min_frac : {0.0, 0.2, 0.35, 0.5}) {
+            SahBuilder b{cull, cq, min_frac, {}, {}};
+            b.items.resize((size_t)n);
+            for (int k = 0; k < n; ++k) b.items[(size_t)k] = k;
+            b.nodes.resize(2 * (size_t)n);
+            const int root = b.build(0, n, 6);
+            emit_wide_tree(s, b.nodes, root);
+            if (std::getenv("RT_B200_DEBUG")) std::fprintf(stderr, "[rt_b200] device tree: min_frac %.2f -> %zu nodes, depth %d, stack need %d\n", min_frac, s.dwide.size(), s.wide_depth, s.stack_need);
+            if (s.stack_need <= 36) break;
         }
     }
 

@@ -312,7 +312,7 @@ RT_DEV void wave_loop(const BvhView& bvh, Src& src, unsigned int* counter, unsig
                     Ray r;
                     float max_t;
                     if (!src.load(item, r, max_t)) item = -1;
-                    else if (trav_begin<ANY>(bvh, s, r, max_t, st)) { src.store(item, s); item = -1; }
+                    else if (trav_begin<ANY>(bvh, s, r, max_t)) { src.store(item, s); item = -1; }
                 }
                 continue;
             }
@@ -324,10 +324,8 @@ RT_DEV void wave_loop(const BvhView& bvh, Src& src, unsigned int* counter, unsig
         if (do_prims) trav_prims<ANY, STATS>(bvh, s, st);
         else if (can_step) {
 #pragma unroll 1
-            for (int k = 0; k < RT_STEPS_PER_VOTE && s.pend == 0u && s.cur != RT_CUR_NONE; ++k) {
-                if (s.sp + 3u * stride > s.sp_end) { trav_overflow<ANY>(bvh, s, st); break; }  // rare: the short stack is full
+            for (int k = 0; k < RT_STEPS_PER_VOTE && s.pend == 0u && s.cur != RT_CUR_NONE; ++k)
                 trav_step<ANY, STATS>(bvh, s, stride, st);
-            }
         }
         if (item >= 0 && s.pend == 0u && s.cur == RT_CUR_NONE) { src.store(item, s); item = -1; }
     }
@@ -367,7 +365,7 @@ RT_DEV void packet_loop(const BvhView& bvh, Src& src, unsigned int* counter, uns
             Ray r;
             float max_t;
             if (!src.load(item, r, max_t)) active = false;
-            else if (trav_begin<ANY>(bvh, s, r, max_t, st)) { src.store(item, s); active = false; }
+            else if (trav_begin<ANY>(bvh, s, r, max_t)) { src.store(item, s); active = false; }
         }
         const bool traversing = active;
         unsigned int alive = __ballot_sync(FULL, active);  // lanes still looking for an answer
@@ -383,32 +381,28 @@ RT_DEV void packet_loop(const BvhView& bvh, Src& src, unsigned int* counter, uns
             const int first = __float_as_int(C.v[0]);
             const unsigned int meta = __float_as_uint(C.v[1]);
             const float qi = C.v[2] * s.imax;
-            bool pass[4], sure[4];
+            bool pass[4];
             float ent[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                wide_child_test(s, X.v[k], X.v[4 + k], Y.v[k], Y.v[4 + k], Z.v[k], Z.v[4 + k], qi, pass[k], sure[k], ent[k]);
+            for (int k = 0; k < 4; ++k) {
+                bool sure;
+                wide_child_test(s, X.v[k], X.v[4 + k], Y.v[k], Y.v[4 + k], Z.v[k], Z.v[4 + k], qi, pass[k], sure, ent[k]);
+            }
             unsigned int pm = ((pass[0] ? 1u : 0u) | (pass[1] ? 2u : 0u) | (pass[2] ? 4u : 0u) | (pass[3] ? 8u : 0u)) & meta;
             if (!in) pm = 0u;
-            const unsigned int sm = (sure[0] ? 1u : 0u) | (sure[1] ? 2u : 0u) | (sure[2] ? 4u : 0u) | (sure[3] ? 8u : 0u);
-            unsigned int ex = pm & ~sm & (meta >> 4);
-            while (ex != 0u) {  // gated children too close to call: the reference's exact test (rare)
-                const int k = __ffs(ex) - 1;
-                ex &= ex - 1u;
-                const float* c = w + k;
-                if (!box_exact_call(__ldg(c), __ldg(c + 8), __ldg(c + 16), __ldg(c + 4), __ldg(c + 12), __ldg(c + 20), s.r)) pm &= ~(1u << k);
-            }
-            const unsigned int b0 = __ballot_sync(FULL, pm & 1u), b1 = __ballot_sync(FULL, pm & 2u);
-            const unsigned int b2 = __ballot_sync(FULL, pm & 4u), b3 = __ballot_sync(FULL, pm & 8u);
+            unsigned int b0 = __ballot_sync(FULL, pm & 1u), b1 = __ballot_sync(FULL, pm & 2u);
+            unsigned int b2 = __ballot_sync(FULL, pm & 4u), b3 = __ballot_sync(FULL, pm & 8u);
+            const unsigned int primmask = (meta >> 4) & 15u;  // warp-uniform: which children are primitives
             bool descended = false;
-            if (meta & WIDE_LEAF_BIT) {
-                // a reference leaf: every candidate primitive is tested by all its lanes together
+            if (primmask != 0u) {
+                // primitive children: every candidate is tested by all its lanes together (each lane behind its own gate)
 #pragma unroll 1
                 for (int k = 0; k < 4; ++k) {
+                    if (!((primmask >> k) & 1u)) continue;
                     const unsigned int bk = (k == 0 ? b0 : (k == 1 ? b1 : (k == 2 ? b2 : b3))) & alive;
                     if (bk == 0u) continue;
-                    const int idx = first + k;
-                    const bool mine = (bk >> lane) & 1u;
+                    const int idx = __float_as_int(k == 0 ? C.v[3] : (k == 1 ? C.v[4] : (k == 2 ? C.v[5] : C.v[6])));
+                    const bool mine = ((bk >> lane) & 1u) && gate_passes(bvh, s, idx);
                     const unsigned int type = (meta >> (16 + 2 * k)) & 3u;  // warp-uniform
                     Hit h;
                     bool hit = false;
@@ -423,8 +417,13 @@ RT_DEV void packet_loop(const BvhView& bvh, Src& src, unsigned int* counter, uns
                     }
                     if (ANY) alive = __ballot_sync(FULL, active);
                 }
-            } else if ((b0 | b1 | b2 | b3) != 0u) {
-                // inner node: children ordered by the packet's smallest entry parameter
+                if (primmask & 1u) b0 = 0u;
+                if (primmask & 2u) b1 = 0u;
+                if (primmask & 4u) b2 = 0u;
+                if (primmask & 8u) b3 = 0u;
+            }
+            if (((b0 | b1 | b2 | b3) & alive) != 0u) {
+                // inner children, ordered by the packet's smallest entry parameter
                 int key[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -433,7 +432,7 @@ RT_DEV void packet_loop(const BvhView& bvh, Src& src, unsigned int* counter, uns
                     if (bk != 0u) {
                         if (ANY && !RT_ANY_SORTED_PACKET) v = k;  // slot order
                         else {
-                            const int mine = ((pm >> k) & 1u) ? __float_as_int(fmaxf(ent[k], 0.0f)) : 0x7fffffff;
+                            const int mine = (((pm >> k) & 1u) != 0u) ? __float_as_int(fmaxf(ent[k], 0.0f)) : 0x7fffffff;
                             v = (__reduce_min_sync(FULL, mine) & ~3) | k;
                         }
                     }
@@ -475,6 +474,34 @@ RT_DEV void packet_loop(const BvhView& bvh, Src& src, unsigned int* counter, uns
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Literal mode (rt_render_params.reserved[0] bit 0, and -bvh off): the reference's own traversal, one thread
+// per ray, nothing shared with the production loops but the intersection routines and the ray sources --
+// BVH::intersect over the reference's binary tree with exact box tests (traverse_reference_impl), or
+// BVH::intersect_linear (traverse_linear_impl). The parity tests hold the production path to this one bit
+// for bit at full benchmark sizes.
+// ---------------------------------------------------------------------------------------------
+template <bool ANY, bool STATS, class Src>
+RT_DEV void literal_loop(const BvhView& bvh, Src& src, unsigned long long n, TraceStats& st) {
+    for (unsigned long long item = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; item < n; item += (unsigned long long)gridDim.x * blockDim.x) {
+        Ray r;
+        float max_t;
+        if (!src.load((long long)item, r, max_t)) continue;
+        TravState s;
+        s.best_prim = -1;
+        s.best_t = FLT_MAX;
+        if (bvh.n_prims > 0) {
+            unsigned int boxes = 0;
+            const int4 v = bvh.use_bvh ? traverse_reference_impl<ANY>(bvh.prims, bvh.ref_tree, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.time, max_t, &boxes)
+                                       : traverse_linear_impl<ANY>(bvh.prims, bvh.n_prims, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.time, max_t);
+            s.best_prim = ANY ? (v.x ? 0 : -1) : v.y;
+            s.best_t = __int_as_float(v.z);
+            if (STATS) { st.prims += (unsigned int)v.w; st.nodes += boxes; }
+        }
+        src.store((long long)item, s);
+    }
+}
+
 RT_DEV void flush_stats(const FrameParams& p, const TraceStats& st) {
     unsigned long long a = st.nodes, b = st.prims;
 #pragma unroll
@@ -506,6 +533,16 @@ __global__ void __launch_bounds__(RT_TRACE_THREADS, RT_TRACE_MINBLOCKS) trace_ke
     TraceStats st = {0u, 0u};
     ViewRays src = {p.q[level & 1], p.hit_prim};
     wave_loop<false, STATS>(p.bvh, src, lv + L_WORK_TRACE, n, st);
+    if (STATS) flush_stats(p, st);
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(128) trace_literal_kernel(const __grid_constant__ FrameParams p, int level) {
+    unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
+    const unsigned int n = min(lv[L_RAYS], (unsigned int)p.capacity);
+    TraceStats st = {0u, 0u};
+    ViewRays src = {p.q[level & 1], p.hit_prim};
+    literal_loop<false, STATS>(p.bvh, src, n, st);
     if (STATS) flush_stats(p, st);
 }
 
@@ -806,6 +843,16 @@ __global__ void __launch_bounds__(RT_TRACE_THREADS, RT_TRACE_MINBLOCKS) shadow_p
     if (STATS) flush_stats(p, st);
 }
 
+template <bool STATS>
+__global__ void __launch_bounds__(128) shadow_literal_kernel(const __grid_constant__ FrameParams p, int level) {
+    unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
+    const unsigned long long n = (unsigned long long)lv[L_RECS] * (unsigned long long)p.shadow_per_rec;
+    TraceStats st = {0u, 0u};
+    ShadowRays src = {p, p.recs[level & 1], p.vis[level & 1], lv[L_RECS], nullptr};
+    literal_loop<true, STATS>(p.bvh, src, n, st);
+    if (STATS) flush_stats(p, st);
+}
+
 // ---------------------------------------------------------------------------------------------
 // light_kernel: Blinn-Phong sum of one shade record with the visibilities from shadow_kernel.
 // shade() raytracer.cpp:191-273, then Trace()'s local_contribution * localColor.
@@ -925,7 +972,7 @@ __global__ void selftest_box_kernel(uint32_t seed, long long n, unsigned long lo
     atomicAdd(out + 4, v1); atomicAdd(out + 5, v2); atomicAdd(out + 6, skipped);
 }
 
-// For every primitive child of every leaf node of the wide tree and `per_prim` rays aimed at / around
+// For every primitive child of every node of the wide tree and `per_prim` rays aimed at / around
 // it: if the exact intersection routine reports a hit, the conservative test of its culling box must
 // pass. out[0] tests, out[1] exact hits, out[2] culling passes, out[3] VIOLATION hit && !pass.
 __global__ void selftest_cull_kernel(BvhView b, int n_nodes, int per_prim, uint32_t seed, float scene_span, unsigned long long* out) {
@@ -935,8 +982,8 @@ __global__ void selftest_cull_kernel(BvhView b, int n_nodes, int per_prim, uint3
         const int node = (int)(i / (4 * per_prim)), k = (int)((i / per_prim) & 3);
         const float* w = b.wide + (size_t)node * 32;
         const unsigned int meta = __float_as_uint(__ldg(w + 25));
-        if (!(meta & WIDE_LEAF_BIT) || !((meta >> k) & 1u)) continue;
-        const int idx = __float_as_int(__ldg(w + 24)) + k;
+        if (!((meta >> k) & 1u) || !((meta >> (4 + k)) & 1u)) continue;  // primitive children only
+        const int idx = __float_as_int(__ldg(w + 27 + k));
         const float lox = __ldg(w + k), hix = __ldg(w + 4 + k), loy = __ldg(w + 8 + k), hiy = __ldg(w + 12 + k), loz = __ldg(w + 16 + k), hiz = __ldg(w + 20 + k);
         if (!(hix - lox < 1e29f)) continue;  // unbounded culling box: never skipped
         const uint32_t lo32 = (uint32_t)i, hi32 = (uint32_t)(i >> 32) ^ seed;
@@ -1053,6 +1100,7 @@ struct DeviceScene {
     float4* prims = nullptr;
     float* wide = nullptr;
     float4* leafbox = nullptr;
+    float* ref_tree = nullptr;   // literal mode only: the reference's binary tree (HostScene::tree), uploaded on first use
     float4* mats = nullptr;
     float4* lights = nullptr;
     DTexture* textures = nullptr;
@@ -1139,6 +1187,7 @@ static void free_device(DeviceScene* d) {
     cudaGetDevice(&cur);
     if (d->device >= 0) cudaSetDevice(d->device);
     cudaFree(d->arena);
+    cudaFree(d->ref_tree);
     cudaFree(d->q[0]); cudaFree(d->q[1]); cudaFree(d->hit_prim);
     for (int i = 0; i < 2; ++i) { cudaFree(d->recs[i]); cudaFree(d->vis[i]); }
     if (d->aux) cudaStreamDestroy(d->aux);
@@ -1242,19 +1291,13 @@ static int device_scene(HostScene& h, DeviceScene** out) {
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
         d->sm_count = prop.multiProcessorCount;
-        // Traversal stacks in shared memory. A ray can need h.stack_need entries (every node of its path pushed
-        // all its other children), but almost none does: the per-ray kernels get RT_B200_STACK_CAP entries per
-        // thread (default 32; measured on configs[1]: 64 -> 24 entries +3 %, 16 entries -35 %: deep stacks are common) -- shared memory not spent on stacks stays L1, which the node loads live on -- and a
-        // ray that runs out finishes in the exact per-lane traversal (traverse_exact_impl, own local stack), which
-        // returns the same (t, shape). The packet kernels keep one full-depth stack per WARP.
-        static const int stack_cap = [] { const char* e = std::getenv("RT_B200_STACK_CAP"); return e ? std::max(4, std::atoi(e)) : 32; }();
-        d->packet_stack_depth = std::max(4, h.stack_need);
-        d->stack_depth = std::min(d->packet_stack_depth, stack_cap);
+        // Traversal stacks in shared memory: h.stack_need entries (bvh.cpp keeps the tree at <= 32 where it can),
+        // per thread in the per-ray kernels, per warp (16-byte entries) in the packet kernels.
+        d->stack_depth = d->packet_stack_depth = std::max(4, h.stack_need);
         d->stack_bytes = (size_t)d->stack_depth * RT_TRACE_THREADS * sizeof(int) * RT_STACK_WORDS;
         d->n_staged = std::min<int>(RT_STAGE_TOP, (int)h.dwide.size());
         d->stack_bytes += (size_t)d->n_staged * sizeof(DWide);
-        if ((size_t)d->packet_stack_depth * 16 * (RT_TRACE_THREADS / 32) > 200 * 1024) { set_error("BVH too deep for the shared-memory traversal stack"); return RT_ERR_SCENE; }
-        if (h.stack_need > 64) { set_error("BVH too deep for the fallback traversal stack (64 entries)"); return RT_ERR_SCENE; }
+        if (d->stack_bytes > 200 * 1024) { set_error("BVH too deep for the shared-memory traversal stack"); return RT_ERR_SCENE; }
         if (d->stack_bytes > 48 * 1024) {
             CUDA_TRY(cudaFuncSetAttribute(trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
             CUDA_TRY(cudaFuncSetAttribute(trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
@@ -1545,8 +1588,12 @@ static int enqueue_frame(const HostScene& h, DeviceScene* d, FrameParams& k, boo
             const bool packets = packet_enabled && level <= packet_levels;
             // the samples of an area light leave one point: coherent at every level
             const bool shadow_packets = packets || (packet_enabled && area_light_packets);
+            const bool literal = !k.bvh.prune || !k.bvh.use_bvh;  // the reference's own traversal / its linear scan
             int pr = mark_begin(0, stream);
-            if (packets) {
+            if (literal) {
+                if (collect) trace_literal_kernel<true><<<grid_wide, 128, 0, stream>>>(k, level);
+                else trace_literal_kernel<false><<<grid_wide, 128, 0, stream>>>(k, level);
+            } else if (packets) {
                 if (collect) trace_packet_kernel<true><<<grid_trace, RT_TRACE_THREADS, packet_smem, stream>>>(k, level);
                 else trace_packet_kernel<false><<<grid_trace, RT_TRACE_THREADS, packet_smem, stream>>>(k, level);
             } else {
@@ -1565,7 +1612,10 @@ static int enqueue_frame(const HostScene& h, DeviceScene* d, FrameParams& k, boo
             }
             if (k.shadow_per_rec > 0) {
                 pr = mark_begin(1, aux);
-                if (shadow_packets) {
+                if (literal) {
+                    if (collect) shadow_literal_kernel<true><<<grid_wide, 128, 0, aux>>>(k, level);
+                    else shadow_literal_kernel<false><<<grid_wide, 128, 0, aux>>>(k, level);
+                } else if (shadow_packets) {
                     if (collect) shadow_packet_kernel<true><<<grid_shadow, RT_TRACE_THREADS, packet_smem, aux>>>(k, level);
                     else shadow_packet_kernel<false><<<grid_shadow, RT_TRACE_THREADS, packet_smem, aux>>>(k, level);
                 } else {
@@ -1624,6 +1674,12 @@ static int render_impl(HostScene& h, const rt_render_params& rp, uint8_t* rgb8, 
     if ((rc = ensure_plan(d, k, rp.reserved[5], stream, &plan)) != RT_OK) return rc;
     if (plan_out) *plan_out = plan;
     k.packed = packed ? 1 : 0;
+    if (!k.bvh.prune && k.bvh.use_bvh && !d->ref_tree && !h.tree.empty()) {
+        static_assert(sizeof(TreeNode) == 40, "RefNode layout of traverse_reference_impl: 10 words per node");
+        CUDA_TRY(cudaMalloc((void**)&d->ref_tree, h.tree.size() * sizeof(TreeNode)));
+        CUDA_TRY(cudaMemcpyAsync(d->ref_tree, h.tree.data(), h.tree.size() * sizeof(TreeNode), cudaMemcpyHostToDevice, stream));
+    }
+    k.bvh.ref_tree = d->ref_tree;
     k.bvh.prims = d->prims; k.bvh.wide = d->wide; k.bvh.leafbox = d->leafbox; k.bvh.stack_depth = d->stack_depth;
     k.bvh.packet_stack_depth = d->packet_stack_depth; k.bvh.n_staged = d->n_staged;
     k.mats = d->mats; k.lights = d->lights; k.textures = d->textures; k.texels = d->texels;
@@ -1962,7 +2018,7 @@ __global__ void __launch_bounds__(RT_TRACE_THREADS, RT_TRACE_MINBLOCKS) trav_pea
     BvhView b = bvh;
     b.prune = 1;
     b.use_bvh = 1;
-    trav_begin<ANY>(b, s, r, 1e30f, st);
+    trav_begin<ANY>(b, s, r, 1e30f);
     unsigned long long acc = 0;
     int node = (int)(gid % (unsigned int)n_nodes);
 #pragma unroll 1
@@ -2113,11 +2169,11 @@ int rt_traversal_peak(rt_scene* scene, int32_t any_hit, int32_t n_nodes, int32_t
     std::memset(&b, 0, sizeof(b));
     b.prims = ds->prims; b.wide = ds->wide; b.leafbox = ds->leafbox; b.n_prims = (int)h.dprims.size(); b.use_bvh = 1; b.prune = 1;
     b.stack_depth = ds->stack_depth;
-    // inner nodes only (a leaf node parks its children in `pend` instead of pushing): the first n nodes in
-    // breadth-first order are the top of the tree
+    // nodes with node children only (primitive children are parked in `pend` instead of pushed): the first n
+    // nodes in breadth-first order are the top of the tree
     int n = 0;
     const int limit = std::min<int>(n_nodes, (int)h.dwide.size());
-    while (n < limit && !(((const uint32_t*)h.dwide[n].f)[25] & rtb::WIDE_LEAF)) ++n;
+    while (n < limit && ((((const uint32_t*)h.dwide[n].f)[25] >> 4) & 15u) == 0u) ++n;
     if (n < 1) n = 1;
     const rtb::Box& box = h.tree[0].box;
     const float3 eye = make_float3(h.cam.location[0], h.cam.location[1], h.cam.location[2]);

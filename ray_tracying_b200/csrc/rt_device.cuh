@@ -11,11 +11,12 @@
 // ray passes, collects ALL leaf hits and returns the first minimum. Ancestor boxes contain leaf
 // boxes and IEEE rounding is monotonic, so a shape is tested iff the box of ITS LEAF passes
 // AABB::intersect. Therefore:
-//   * inner boxes only need a CONSERVATIVE test (never rejects what the reference accepts):
-//     6 FMAs with a precomputed reciprocal instead of 6 IEEE divisions;
-//   * the box of a reference leaf ("gated" child) gets the conservative test first and, when the
-//     outcome is too close to call, the EXACT reference test;
-//   * a primitive's own (padded) culling box may skip its test when the ray clearly misses it;
+//   * that condition is evaluated PER PRIMITIVE ("gate"): the exact box of the primitive's reference
+//     leaf gets a conservative test first and, when the outcome is too close to call, the reference's
+//     exact test (gate_passes());
+//   * every box of the device tree is a CULLING box (a primitive's padded box or a union of such):
+//     it only needs a CONSERVATIVE test -- never rejects a ray for which the primitive's routine
+//     could report a hit -- 6 FMAs with a precomputed reciprocal instead of 6 IEEE divisions;
 //   * visiting near-first and skipping sub-trees that start beyond the best hit (plus a margin
 //     four orders above rounding noise) cannot change the (t, shape) result.
 #pragma once
@@ -283,6 +284,7 @@ struct BvhView {
     const float4* __restrict__ prims;
     const float* __restrict__ wide;  // 32 floats per node
     const float4* __restrict__ leafbox;  // 2 x float4 per primitive: exact box of its reference leaf
+    const float* __restrict__ ref_tree;  // literal mode only: the reference's binary tree, 10 words per node (RefNode)
     int n_prims;
     int use_bvh;
     int prune;        // 0: visit everything, exact tests only (the reference's literal traversal)
@@ -300,7 +302,6 @@ struct TraceStats {
 // (~1e-7 relative), four orders below this margin.
 RT_DEV float prune_limit(float best_t) { return best_t * 1.0001f + 1e-4f; }
 
-#define WIDE_LEAF_BIT 0x100u  // scene.hpp WIDE_LEAF
 
 struct F8 { float v[8]; };
 // One 256-bit read-only load (sm_100: LDG.E.256): a quarter of a wide node per instruction, i.e.
@@ -365,64 +366,44 @@ __device__ __noinline__ int4 traverse_linear_impl(const float4* __restrict__ pri
     return make_int4(0, best_prim, __float_as_int(best_t), tests);
 }
 
-// Exact traversal of the wide tree, one lane on its own: the reference's exact box test on every
-// child, no culling boxes, every primitive of every reference leaf whose box passes is tested.
-//   PRUNE = false: the reference's literal traversal (no ordering, no pruning) -- the prune = 0
-//                  validation mode;
-//   PRUNE = true : near-first order and t-pruning with the exact test's own entry parameter --
-//                  for rays the conservative test cannot handle (a direction component with
-//                  |d| <= 1e-6, where the reference tests containment instead of dividing).
+// BVH::intersect / intersect_helper (acceleration.cpp:67-117), literally: the reference's own binary tree
+// (RefNode = TreeNode of scene.hpp: box lo[3] hi[3], left, right, first, count), the exact box test at every
+// node, both children visited, every shape of every leaf reached tested, first minimum of t. This is the
+// prune = 0 validation mode; it shares nothing with the production traversal but the intersection routines.
 // Returns (occluded, best_prim, bits best_t, primitive tests); box tests in `boxes`.
-template <bool ANY, bool PRUNE>
-__device__ __noinline__ int4 traverse_exact_impl(const float4* __restrict__ prims, const float* __restrict__ wide, float ox,
-                                                 float oy, float oz, float dx, float dy, float dz, float time, float max_t,
-                                                 unsigned int* boxes) {
+template <bool ANY>
+__device__ __noinline__ int4 traverse_reference_impl(const float4* __restrict__ prims, const float* __restrict__ ref_tree, float ox,
+                                                     float oy, float oz, float dx, float dy, float dz, float time, float max_t,
+                                                     unsigned int* boxes) {
     Ray r;
     r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz; r.time = time;
     float best_t = FLT_MAX;
-    float lim = (PRUNE && ANY) ? prune_limit(max_t) : FLT_MAX;
     int best_prim = -1, tests = 0;
     unsigned int nb = 0;
     int stack[64];
-    float entry[64];
     int sp = 0;
-    stack[sp] = 0;
-    entry[sp++] = -FLT_MAX;
+    stack[sp++] = 0;
     while (sp > 0) {
-        --sp;
-        if (PRUNE && entry[sp] > lim) continue;
-        const float* w = wide + (size_t)stack[sp] * 32;
-        const int first = __float_as_int(__ldg(w + 24));
-        const unsigned int meta = __float_as_uint(__ldg(w + 25));
-        int child[4];
-        float tn[4];
-        int n = 0;
-        for (int k = 0; k < 4; ++k) {
-            if (!((meta >> k) & 1u)) continue;
-            if (meta & WIDE_LEAF_BIT) {
+        const float* nd = ref_tree + (size_t)stack[--sp] * 10;
+        float t;
+        nb++;
+        if (!box_exact(__ldg(nd + 0), __ldg(nd + 1), __ldg(nd + 2), __ldg(nd + 3), __ldg(nd + 4), __ldg(nd + 5), r, t)) continue;
+        const int left = __float_as_int(__ldg(nd + 6)), right = __float_as_int(__ldg(nd + 7));
+        if (left < 0) {
+            const int first = __float_as_int(__ldg(nd + 8)), count = __float_as_int(__ldg(nd + 9));
+            for (int k = 0; k < count; ++k) {
                 Hit h;
                 tests++;
                 const int idx = first + k;
                 if (intersect_prim<false>(prims, idx, r, h)) {
                     if (ANY) { if (!(h.t > max_t)) { *boxes = nb; return make_int4(1, idx, __float_as_int(h.t), tests); } }
-                    else if (h.t < best_t || (h.t == best_t && idx < best_prim)) {
-                        best_t = h.t; best_prim = idx;
-                        if (PRUNE) lim = prune_limit(best_t);
-                    }
-                }
-            } else {
-                float t;
-                nb++;
-                if (box_exact(__ldg(w + k), __ldg(w + 8 + k), __ldg(w + 16 + k), __ldg(w + 4 + k), __ldg(w + 12 + k),
-                              __ldg(w + 20 + k), r, t) && !(PRUNE && t > lim)) {
-                    int j = n++;  // insertion sort, farthest first
-                    while (PRUNE && j > 0 && tn[j - 1] < t) { tn[j] = tn[j - 1]; child[j] = child[j - 1]; --j; }
-                    tn[j] = t;
-                    child[j] = first + k;
+                    else if (h.t < best_t || (h.t == best_t && idx < best_prim)) { best_t = h.t; best_prim = idx; }
                 }
             }
+        } else if (sp + 2 <= 64) {
+            stack[sp++] = right;
+            stack[sp++] = left;
         }
-        for (int j = 0; j < n && sp < 64; ++j) { stack[sp] = child[j]; entry[sp++] = tn[j]; }
     }
     *boxes = nb;
     return make_int4(0, best_prim, __float_as_int(best_t), tests);
@@ -445,9 +426,15 @@ __device__ __noinline__ int4 traverse_exact_impl(const float4* __restrict__ prim
 //   pass   : tn' - tf' <= slack        and  tf' >= -slack       (never rejects what the reference accepts)
 //   surely : tn' - tf' <= -slack - KS  and  tf' >=  slack + KS  (the reference's exact test passes;
 //            KS = 4 max_i e_i undoes the padding of the addends)
-// A gated child (exact box of a reference leaf) that passes but not surely gets the exact test.
-// Rays with a direction component |d_i| <= 1e-6 (the reference's "parallel" rule) never come
-// here (traverse_exact_impl).
+// The GATE of a primitive (exact box of its reference leaf) that passes but not surely gets the exact test.
+//
+// Rays with a direction component |d_i| <= 1e-6: the reference's box test then only asks whether the
+// origin lies inside the slab (its "parallel" rule), whatever the other axes say -- neither a superset nor
+// a subset of the slab test. So for such rays the gate is always decided by the exact test (KS is set to
+// infinity), while the culling boxes -- which bound where the primitive's routine can report a hit, i.e.
+// geometry -- keep the slab test with the ray's true reciprocal, clamped to +-1e30 so that no product
+// overflows (a component below 1e-30 moves the ray by less than 1e-24 over any scene: it is treated as
+// zero, with an absolute e_i of 1e20 that turns the slab test into "origin inside the slab, to 1e-10").
 // ---------------------------------------------------------------------------------------------
 #define RT_CUR_NONE (-1)
 
@@ -511,10 +498,9 @@ struct TravState {
     unsigned int staged;  // RT_STAGE_TOP: shared-space address of the staged top nodes
 };
 
-// Sets up a ray. Returns true when the ray is already finished (empty scene, linear scan, exact
-// path); s.best_prim then holds the answer.
+// Sets up a ray. Returns true when the ray is already finished (empty scene).
 template <bool ANY>
-RT_DEV bool trav_begin(const BvhView& b, TravState& s, const Ray& r, float max_t, TraceStats& st) {
+RT_DEV bool trav_begin(const BvhView& b, TravState& s, const Ray& r, float max_t) {
     s.r = r;
     s.max_t = max_t;
     s.best_t = FLT_MAX;
@@ -524,32 +510,23 @@ RT_DEV bool trav_begin(const BvhView& b, TravState& s, const Ray& r, float max_t
     s.pend = 0u;
     s.pend_node = 0;
     if (b.n_prims == 0) return true;
-    if (!b.use_bvh) {
-        const int4 v = traverse_linear_impl<ANY>(b.prims, b.n_prims, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.time, max_t);
-        s.best_prim = ANY ? (v.x ? 0 : -1) : v.y;
-        s.best_t = __int_as_float(v.z);
-        st.prims += (unsigned int)v.w;
-        return true;
-    }
-    const bool slow = fabsf(r.dx) <= 1e-6f || fabsf(r.dy) <= 1e-6f || fabsf(r.dz) <= 1e-6f;
-    if (slow || !b.prune) {
-        unsigned int boxes = 0;
-        const int4 v = b.prune ? traverse_exact_impl<ANY, true>(b.prims, b.wide, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.time, max_t, &boxes)
-                               : traverse_exact_impl<ANY, false>(b.prims, b.wide, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.time, max_t, &boxes);
-        s.best_prim = ANY ? (v.x ? 0 : -1) : v.y;
-        s.best_t = __int_as_float(v.z);
-        st.prims += (unsigned int)v.w;
-        st.nodes += boxes;
-        return true;
-    }
+    const float BIG = 1e30f;
     s.ix = 1.0f / r.dx; s.iy = 1.0f / r.dy; s.iz = 1.0f / r.dz;
+    const bool cx = !(fabsf(s.ix) <= BIG), cy = !(fabsf(s.iy) <= BIG), cz = !(fabsf(s.iz) <= BIG);
+    if (cx) s.ix = copysignf(BIG, r.dx);
+    if (cy) s.iy = copysignf(BIG, r.dy);
+    if (cz) s.iz = copysignf(BIG, r.dz);
     const float nx = -(r.ox * s.ix), ny = -(r.oy * s.iy), nz = -(r.oz * s.iz);
-    const float ex = 1.2e-7f * fabsf(nx) + 1e-35f, ey = 1.2e-7f * fabsf(ny) + 1e-35f, ez = 1.2e-7f * fabsf(nz) + 1e-35f;
+    float ex = 1.2e-7f * fabsf(nx) + 1e-35f, ey = 1.2e-7f * fabsf(ny) + 1e-35f, ez = 1.2e-7f * fabsf(nz) + 1e-35f;
+    if (cx) ex = fmaxf(ex, 1e20f);
+    if (cy) ey = fmaxf(ey, 1e20f);
+    if (cz) ez = fmaxf(ez, 1e20f);
     // d_i > 0: the lo plane is the entry plane (pad it towards -inf), the hi plane the exit plane
     s.nxl = s.ix > 0.0f ? nx - ex : nx + ex; s.nxh = s.ix > 0.0f ? nx + ex : nx - ex;
     s.nyl = s.iy > 0.0f ? ny - ey : ny + ey; s.nyh = s.iy > 0.0f ? ny + ey : ny - ey;
     s.nzl = s.iz > 0.0f ? nz - ez : nz + ez; s.nzh = s.iz > 0.0f ? nz + ez : nz - ez;
-    s.KS = 4.0f * fmaxf(fmaxf(ex, ey), ez);
+    const bool parallel = fabsf(r.dx) <= 1e-6f || fabsf(r.dy) <= 1e-6f || fabsf(r.dz) <= 1e-6f;
+    s.KS = parallel ? __int_as_float(0x7f800000) : 4.0f * fmaxf(fmaxf(ex, ey), ez);
     s.imax = fmaxf(fmaxf(fabsf(s.ix), fabsf(s.iy)), fabsf(s.iz));
     s.lim = ANY ? prune_limit(max_t) : FLT_MAX;
     s.cur = 0;
@@ -575,7 +552,7 @@ RT_DEV void wide_child_test(const TravState& s, float lox, float hix, float loy,
 }
 
 // Visits node s.cur: tests its (up to) four children. Node children are pushed far-to-near and
-// the nearest becomes s.cur; primitive children (a reference leaf's node) become s.pend. The
+// the nearest becomes s.cur; primitive children whose culling box passes become s.pend. The
 // caller guarantees s.cur != RT_CUR_NONE and s.pend == 0. `stride` = bytes between two stack entries
 // of a thread. Written to compile to straight-line predicated code.
 template <bool ANY, bool STATS>
@@ -597,28 +574,21 @@ RT_DEV void trav_step(const BvhView& b, TravState& s, unsigned int stride, Trace
     const int first = __float_as_int(C.v[0]);
     const unsigned int meta = __float_as_uint(C.v[1]);
     const float qi = C.v[2] * s.imax;
-    bool pass[4], sure[4];
+    bool pass[4];
     float ent[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-        wide_child_test(s, X.v[k], X.v[4 + k], Y.v[k], Y.v[4 + k], Z.v[k], Z.v[4 + k], qi, pass[k], sure[k], ent[k]);
-    unsigned int pm = ((pass[0] ? 1u : 0u) | (pass[1] ? 2u : 0u) | (pass[2] ? 4u : 0u) | (pass[3] ? 8u : 0u)) & meta;
-    // gated children that pass but not surely: the reference's exact test decides (rare)
-    const unsigned int sm = (sure[0] ? 1u : 0u) | (sure[1] ? 2u : 0u) | (sure[2] ? 4u : 0u) | (sure[3] ? 8u : 0u);
-    unsigned int ex = pm & ~sm & (meta >> 4);
-    while (ex != 0u) {
-        const int k = __ffs(ex) - 1;
-        ex &= ex - 1u;
-        const float* c = w + k;
-        if (!box_exact_call(__ldg(c), __ldg(c + 8), __ldg(c + 16), __ldg(c + 4), __ldg(c + 12), __ldg(c + 20), s.r)) pm &= ~(1u << k);
+    for (int k = 0; k < 4; ++k) {
+        bool sure;  // unused for culling boxes: dead code after inlining
+        wide_child_test(s, X.v[k], X.v[4 + k], Y.v[k], Y.v[4 + k], Z.v[k], Z.v[4 + k], qi, pass[k], sure, ent[k]);
     }
+    unsigned int pm = ((pass[0] ? 1u : 0u) | (pass[1] ? 2u : 0u) | (pass[2] ? 4u : 0u) | (pass[3] ? 8u : 0u)) & meta;
     int next = RT_CUR_NONE;
     unsigned int sp = s.sp;
-    if (meta & WIDE_LEAF_BIT) {
-        // a reference leaf's node: its passing children wait for the warp's next primitive phase
-        s.pend = pm;
-        s.pend_node = node;
-    } else if (ANY && !RT_ANY_SORTED) {
+    // primitive children whose culling box passes wait for the warp's next primitive phase
+    s.pend = pm & (meta >> 4);
+    s.pend_node = node;
+    pm &= ~(meta >> 4);
+    if (ANY && !RT_ANY_SORTED) {
         // occlusion query: order does not matter
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -663,30 +633,20 @@ RT_DEV void trav_step(const BvhView& b, TravState& s, unsigned int stride, Trace
     s.cur = next;
 }
 
-// The short shared-memory stack of a per-ray kernel cannot take another node's children: the ray starts
-// over in the exact per-lane traversal (near-first, t-pruning, its own 64-entry local stack), which returns
-// the same (t, first shape among equal t) -- the result does not depend on visit order or on which
-// conservative tests were used on the way.
-// (inlined wrapper around the out-of-line traversal, which takes the ray by value: a reference parameter of a
-// real call would pin the caller's ray state in local memory)
-#ifndef RT_OVERFLOW_NOINLINE
-#define RT_OVERFLOW_NOINLINE 0
-#endif
-template <bool ANY>
-#if RT_OVERFLOW_NOINLINE
-__device__ __noinline__ void trav_overflow(const BvhView& b, TravState& s, TraceStats& st) {
-#else
-RT_DEV void trav_overflow(const BvhView& b, TravState& s, TraceStats& st) {
-#endif
-    unsigned int boxes = 0;
-    const int4 v = traverse_exact_impl<ANY, true>(b.prims, b.wide, s.r.ox, s.r.oy, s.r.oz, s.r.dx, s.r.dy, s.r.dz, s.r.time, s.max_t, &boxes);
-    s.best_prim = ANY ? (v.x ? 0 : -1) : v.y;
-    s.best_t = __int_as_float(v.z);
-    st.prims += (unsigned int)v.w;
-    st.nodes += boxes;
-    s.cur = RT_CUR_NONE;
-    s.sp = s.sp0;
-    s.pend = 0u;
+// The gate of primitive `idx` (sorted position): does the exact box of its reference leaf pass the
+// reference's AABB::intersect for this ray? Conservative test first; the reference's own arithmetic
+// (out of line, rare) when that is too close to call, and always for rays with a component |d_i| <= 1e-6
+// (KS = infinity, see the comment above TravState).
+RT_DEV bool gate_passes(const BvhView& b, const TravState& s, int idx) {
+    const float4 lo = __ldg(b.leafbox + 2 * (size_t)idx), hi = __ldg(b.leafbox + 2 * (size_t)idx + 1);
+    if (!(s.KS > 3e38f)) {
+        bool pass, sure;
+        float ent;
+        wide_child_test(s, lo.x, hi.x, lo.y, hi.y, lo.z, hi.z, 0.0f, pass, sure, ent);
+        if (!pass) return false;  // the reference's test cannot pass (or the leaf starts beyond the best hit)
+        if (sure) return true;    // ... cannot fail
+    }
+    return box_exact_call(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, s.r);
 }
 
 // The warp's primitive phase: every lane with pending primitives tests them, one class of
@@ -695,10 +655,8 @@ RT_DEV void trav_overflow(const BvhView& b, TravState& s, TraceStats& st) {
 template <bool ANY, bool STATS>
 RT_DEV void trav_prims(const BvhView& b, TravState& s, TraceStats& st) {
     unsigned int m_x = 0u, m_p = 0u;
-    int first = 0;
+    const float* w = b.wide + (size_t)s.pend_node * 32;
     if (s.pend != 0u) {
-        const float* w = b.wide + (size_t)s.pend_node * 32;
-        first = __float_as_int(__ldg(w + 24));
         const unsigned int t = __float_as_uint(__ldg(w + 25)) >> 16;  // 2 bits of type per child
         const unsigned int pl = ((t & 3u) == 3u ? 1u : 0u) | (((t >> 2) & 3u) == 3u ? 2u : 0u) | (((t >> 4) & 3u) == 3u ? 4u : 0u) |
                                 (((t >> 6) & 3u) == 3u ? 8u : 0u);
@@ -709,30 +667,36 @@ RT_DEV void trav_prims(const BvhView& b, TravState& s, TraceStats& st) {
     bool occluded = false;
     while (__any_sync(0xffffffffu, m_x != 0u)) {
         if (m_x != 0u) {
-            const int idx = first + __ffs(m_x) - 1;
+            const int k = __ffs(m_x) - 1;
             m_x &= m_x - 1u;
+            const int idx = __float_as_int(__ldg(w + 27 + k));
             Hit h;
-            if (STATS) st.prims++;
-            if (intersect_prim<false, PRIM_XFORM>(b.prims, idx, s.r, h)) {
-                if (ANY) {
-                    if (!(h.t > s.max_t)) { occluded = true; m_x = 0u; m_p = 0u; }
-                } else if (h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) {
-                    s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
+            if (gate_passes(b, s, idx)) {
+                if (STATS) st.prims++;
+                if (intersect_prim<false, PRIM_XFORM>(b.prims, idx, s.r, h)) {
+                    if (ANY) {
+                        if (!(h.t > s.max_t)) { occluded = true; m_x = 0u; m_p = 0u; }
+                    } else if (h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) {
+                        s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
+                    }
                 }
             }
         }
     }
     while (__any_sync(0xffffffffu, m_p != 0u)) {
         if (m_p != 0u) {
-            const int idx = first + __ffs(m_p) - 1;
+            const int k = __ffs(m_p) - 1;
             m_p &= m_p - 1u;
+            const int idx = __float_as_int(__ldg(w + 27 + k));
             Hit h;
-            if (STATS) st.prims++;
-            if (intersect_prim<false, PRIM_PLANE>(b.prims, idx, s.r, h)) {
-                if (ANY) {
-                    if (!(h.t > s.max_t)) { occluded = true; m_p = 0u; }
-                } else if (h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) {
-                    s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
+            if (gate_passes(b, s, idx)) {
+                if (STATS) st.prims++;
+                if (intersect_prim<false, PRIM_PLANE>(b.prims, idx, s.r, h)) {
+                    if (ANY) {
+                        if (!(h.t > s.max_t)) { occluded = true; m_p = 0u; }
+                    } else if (h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) {
+                        s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
+                    }
                 }
             }
         }

@@ -284,12 +284,15 @@ void load_lights(const Value& root, std::vector<rt_light_desc>& lights) {
 }
 
 // One element of "spheres" / "cubes" / "rectangles" / "planes" after conversion (json_loader.cpp:180-332).
+// The primitive is written straight into its slot of HostScene::prims; what the serial pass still needs
+// (material record, texture name, warnings) travels here.
 struct ShapeOut {
     bool ok = false;
-    HostPrim prim;             // material = -1 until the serial pass interns `mat`
+    HostPrim& prim;            // material = -1 until the serial pass interns `mat`
     rt_material_desc mat;
     std::string texture_file;  // resolved in the serial pass
     std::string warn;          // what the reference would have printed for this element
+    explicit ShapeOut(HostPrim& slot) : prim(slot) {}
 };
 
 void convert_shape(int type, const Value& j, ShapeOut& o) {
@@ -378,8 +381,14 @@ void load_shapes(const std::vector<jsonmin::DeferredArray>& arrays, HostScene& s
         for (const jsonmin::DeferredArray& a : arrays) if (a.key == keys[c]) arr = &a;
         if (!arr || arr->elements.empty()) continue;
         const size_t n = arr->elements.size();
-        std::vector<ShapeOut> out(n);
+        const size_t base = s.prims.size();
+        s.prims.resize(base + n);
+        // per element: ok flag, material record; texture names and warnings are rare and kept per thread
+        std::vector<uint8_t> ok(n, 0);
+        std::vector<rt_material_desc> mat(n);
+        struct Note { size_t i; std::string texture_file, warn; };
         const unsigned threads = (unsigned)std::max<size_t>(1, std::min<size_t>(host_threads(), n / 2048 + 1));
+        std::vector<std::vector<Note>> notes(threads);
         std::vector<std::string> fatal(threads);
         auto work = [&](unsigned t) {
             const size_t lo = n * t / threads, hi = n * (t + 1) / threads;
@@ -391,7 +400,11 @@ void load_shapes(const std::vector<jsonmin::DeferredArray>& arrays, HostScene& s
                     if (fatal[t].empty()) fatal[t] = e.what();
                     return;
                 }
-                convert_shape(types[c], j, out[i]);
+                ShapeOut o(s.prims[base + i]);
+                convert_shape(types[c], j, o);
+                ok[i] = o.ok ? 1 : 0;
+                mat[i] = o.mat;
+                if (!o.texture_file.empty() || !o.warn.empty()) notes[t].push_back({i, std::move(o.texture_file), std::move(o.warn)});
             }
         };
         std::vector<std::thread> pool;
@@ -399,13 +412,20 @@ void load_shapes(const std::vector<jsonmin::DeferredArray>& arrays, HostScene& s
         work(0);
         for (std::thread& th : pool) th.join();
         for (const std::string& f : fatal) if (!f.empty()) throw std::runtime_error(f);
-        for (ShapeOut& o : out) {
-            if (!o.warn.empty()) std::cerr << o.warn << std::flush;
-            if (!o.ok) continue;
-            if (!o.texture_file.empty()) o.mat.texture = textures.load(o.texture_file);
-            o.prim.material = mats.intern(o.mat);
-            s.prims.push_back(o.prim);
+        // serial, in element order: warnings, textures and materials (their ids depend on first use), compaction
+        unsigned nt = 0;
+        size_t ni = 0, kept = base;
+        for (size_t i = 0; i < n; ++i) {
+            while (nt < threads && ni >= notes[nt].size()) { ++nt; ni = 0; }
+            const Note* note = (nt < threads && notes[nt][ni].i == i) ? &notes[nt][ni++] : nullptr;
+            if (note && !note->warn.empty()) std::cerr << note->warn << std::flush;
+            if (!ok[i]) continue;
+            if (note && !note->texture_file.empty()) mat[i].texture = textures.load(note->texture_file);
+            if (kept != base + i) s.prims[kept] = s.prims[base + i];
+            s.prims[kept].material = mats.intern(mat[i]);
+            ++kept;
         }
+        s.prims.resize(kept);
     }
     if (s.prims.empty()) std::cerr << "Warning: No valid shapes were loaded." << std::endl;
 }

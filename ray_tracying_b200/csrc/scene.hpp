@@ -33,23 +33,20 @@ struct alignas(128) DPrim { F4 q[8]; };
 //   f[ 0.. 3] = lo.x of children 0..3    f[ 4.. 7] = hi.x
 //   f[ 8..11] = lo.y                     f[12..15] = hi.y
 //   f[16..19] = lo.z                     f[20..23] = hi.z
-//   f[24] = bits: index of child 0 -- the children of a node are CONSECUTIVE (wide nodes
-//           first, first + 1, ... or sorted primitive positions first, first + 1, ...), valid
-//           children occupy slots 0..n-1
-//   f[25] = bits: meta = valid mask (bits 0-3) | gate mask (bits 4-7) | WIDE_LEAF (bit 8) |
+//   f[24] = bits: node index of child 0 -- the INNER children of a node occupy slots 0..ni-1 and are
+//           consecutive nodes (first + slot); primitive children follow in slots ni..n-1
+//   f[25] = bits: meta = valid mask (bits 0-3) | primitive mask (bits 4-7: the child is a primitive) |
 //           primitive types, 2 bits per child (bits 16-23)
-//   f[26] = Q: quadratic cull coefficient of the node's spheres (max over children, else 0)
-//   f[27..31] unused
-// The wide tree is the reference's binary tree (acceleration.cpp:20-64) with every other level
-// skipped; the reference tree itself is kept on the host (tie-break order, leaf boxes, tests).
-//   * inner node: children are wide nodes; a child whose gate bit is set has the EXACT box of a
-//     reference leaf: its primitives may only be tested if that box passes the reference's
-//     AABB::intersect (decided exactly when the conservative test is too close to call);
-//   * WIDE_LEAF node = one reference leaf: children are its primitives, each with its own box
-//     pushed outward (a culling box, see bvh.cpp cull_pad); Q = the coefficient of the
-//     distance-squared rounding term of the sphere test.
+//   f[26] = Q: quadratic cull coefficient (largest over the spheres BELOW this node, else 0)
+//   f[27..30] = bits: sorted position of the primitive in slot 0..3 (primitive children only)
+//   f[31] unused
+// The tree is a 4-wide BVH over the primitives' CULLING boxes (bvh.cpp: SAH build, cull_pad); a box
+// of this tree is only ever used to skip work. The reference's own condition for testing a shape --
+// the exact box of its reference leaf passes AABB::intersect -- is evaluated per primitive on
+// HostScene::dleafbox (the "gate"). The reference tree itself stays on the host (sort order for
+// tie-breaks, leaf boxes, tests) and is uploaded only for the literal validation mode.
 struct alignas(128) DWide { float f[32]; };
-constexpr uint32_t WIDE_LEAF = 0x100u;
+constexpr uint32_t WIDE_PRIM_SHIFT = 4;  // meta >> 4 & 15 = primitive mask
 
 // Material = 64 bytes:
 //   m0 = (diffuse.rgb, k_ambient) m1 = (specular.rgb, k_diffuse)

@@ -180,22 +180,19 @@ def test_cli_usage_error_matches_reference(rt):
 
 
 @pytest.mark.parametrize("name", ["mixed_400", "few_3", "few_5", "ties_axis_aligned", "numerics_edge", "textured_40", "ascii_scene"])
-def test_wide_tree_encodes_the_reference_tree(rt, name):
-    """The flattened 4-wide device tree (csrc/scene.hpp DWide) against the reference tree it is built from:
-    every reference leaf is exactly one leaf node whose primitives are the leaf's (consecutive sorted positions);
-    a gated child carries the reference leaf's box bit for bit; every child box contains the boxes below it;
-    children are consecutive; the stack bound 3 * (depth - 1) + 1 holds."""
+def test_wide_tree_covers_every_primitive_once(rt, name):
+    """The flattened 4-wide device tree (csrc/scene.hpp DWide) is a BVH over the primitives' culling boxes: every
+    sorted position is the child of exactly one node; the inner children of a node are consecutive nodes in the
+    leading slots, primitive children follow; every child box contains the boxes below it; the culling boxes of a
+    reference leaf's primitives cover that leaf's box (each contains its primitive's box, whose union the leaf
+    box is); nodes are numbered breadth-first; no ray can need more than 32 stack entries."""
     scene = rt.Scene.from_json(os.path.join(GOLDEN, name + ".json"), GOLDEN)
     nodes, depth = scene.dump_wide()
     ref = scene.dump_bvh()  # pre-order reference nodes: (is_leaf, lo, hi, prims in load order)
     order = scene.shape_order()
     pos_of = {int(load): pos for pos, load in enumerate(order)}
-    ref_leaves = {}
-    for is_leaf, lo, hi, prims in ref:
-        if is_leaf:
-            ref_leaves[pos_of[prims[0]]] = (np.float32(lo), np.float32(hi), [pos_of[p] for p in prims])
     bits = nodes.view(np.uint32)
-    seen_leaves, max_sp = set(), [0]
+    seen, max_sp, levels = {}, [0], {}
 
     def box(n, k):
         f = nodes[n]
@@ -203,32 +200,27 @@ def test_wide_tree_encodes_the_reference_tree(rt, name):
 
     def visit(n, level, sp):
         """returns (lo, hi) of everything below node n; sp = stack entries in use when n is visited"""
+        levels[n] = level
         first, meta = int(bits[n, 24]), int(bits[n, 25])
-        valid = meta & 15
+        valid, prim = meta & 15, (meta >> 4) & 15
         assert valid in (1, 3, 7, 15), "valid children occupy slots 0..n-1"
         cnt = bin(valid).count("1")
+        ni = cnt - bin(prim).count("1")
+        assert prim & ~valid == 0 and prim == (valid & ~((1 << ni) - 1)), "inner children lead, primitives follow"
+        assert level <= depth
+        max_sp[0] = max(max_sp[0], sp + max(0, ni - 1))
         lo_all, hi_all = np.full(3, np.inf), np.full(3, -np.inf)
-        if meta & 0x100:  # leaf node = one reference leaf
-            assert first in ref_leaves and first not in seen_leaves
-            seen_leaves.add(first)
-            rlo, rhi, prims = ref_leaves[first]
-            assert prims == list(range(first, first + cnt))
-            for k in range(cnt):
-                lo, hi = box(n, k)
-                lo_all, hi_all = np.minimum(lo_all, lo), np.maximum(hi_all, hi)
-            assert (lo_all <= rlo).all() and (hi_all >= rhi).all(), "culling boxes cover the leaf box"
-            return rlo, rhi
-        assert level < depth
-        max_sp[0] = max(max_sp[0], sp + cnt - 1)
         for k in range(cnt):
-            child = first + k
             lo, hi = box(n, k)
-            clo, chi = visit(child, level + 1, sp + (cnt - 1 - k if k < cnt - 1 else 0))
-            assert (lo <= clo).all() and (hi >= chi).all(), "a child box contains what is below it"
-            gated = bool((meta >> 4) & (1 << k))
-            assert gated == bool(int(bits[child, 25]) & 0x100), "gate bit <=> the child is a reference leaf"
-            if gated:
-                assert np.array_equal(lo.view(np.uint32), clo.view(np.uint32)) and np.array_equal(hi.view(np.uint32), chi.view(np.uint32))
+            assert (lo <= hi).all()
+            if k < ni:
+                clo, chi = visit(first + k, level + 1, sp + (ni - 1 - k if k < ni - 1 else 0))
+                assert (lo <= clo).all() and (hi >= chi).all(), "a child box contains what is below it"
+            else:
+                pos = int(bits[n, 27 + k])
+                assert pos not in seen, "a primitive appears once"
+                seen[pos] = (lo, hi)
+                assert ((meta >> (16 + 2 * k)) & 3) in (0, 1, 2, 3)
             lo_all, hi_all = np.minimum(lo_all, lo), np.maximum(hi_all, hi)
         return lo_all, hi_all
 
@@ -236,8 +228,18 @@ def test_wide_tree_encodes_the_reference_tree(rt, name):
         assert len(nodes) == 0
         return
     visit(0, 1, 0)
-    assert seen_leaves == set(ref_leaves), "every reference leaf is reachable exactly once"
-    assert max_sp[0] <= 3 * (depth - 1) + 1
+    assert sorted(seen) == list(range(len(order))), "every sorted position is reachable exactly once"
+    assert max_sp[0] + 1 <= 32
+    bfs = [levels[n] for n in range(len(nodes))]
+    assert bfs == sorted(bfs), "breadth-first numbering: levels do not decrease with the node index"
+    for is_leaf, lo, hi, prims in ref:
+        if not is_leaf:
+            continue
+        pos = [pos_of[p] for p in prims]
+        assert pos == list(range(pos[0], pos[0] + len(pos))), "a reference leaf holds consecutive sorted positions"
+        clo = np.min([seen[q][0] for q in pos], axis=0)
+        chi = np.max([seen[q][1] for q in pos], axis=0)
+        assert (clo <= np.float32(lo)).all() and (chi >= np.float32(hi)).all(), "culling boxes cover the leaf box"
 
 
 def test_json_numbers_are_strtod_exact(rt):
