@@ -268,8 +268,7 @@ void set_child_box(DWide& w, int c, const Box& b) {
 // visits about a third fewer nodes: the level of "leaf nodes" (4 culling boxes behind every leaf box) is gone.
 // ---------------------------------------------------------------------------------------------
 struct UpNode {
-    Box box;
-    float q = 0.0f;             // largest sphere cull coefficient below
+    Box box;                    // union of the ANCESTOR boxes (see flatten_scene) of the primitives below
     int left = -1, right = -1;  // UpNode indices; -1 for a leaf
     int prim = -1;              // sorted position of the primitive (leaves only)
 };
@@ -284,8 +283,7 @@ inline void box_merge(Box& b, const Box& o) {
 }
 
 struct SahBuilder {
-    const std::vector<Box>& cull;   // culling box per sorted position
-    const std::vector<float>& cq;   // sphere coefficient per sorted position
+    const std::vector<Box>& cull;   // ancestor box per sorted position (what the inner nodes must contain)
     double min_frac;                // a split must leave at least this share of the primitives on each side
     std::vector<int> items;         // sorted positions, permuted in place
     std::vector<UpNode> nodes;      // pre-sized to 2n - 1: sub-trees built on other threads claim slots with `next`
@@ -299,7 +297,7 @@ struct SahBuilder {
         const int me = alloc();
         UpNode n;
         box_reset(n.box);
-        for (int k = lo; k < hi; ++k) { box_merge(n.box, cull[(size_t)items[k]]); n.q = std::max(n.q, cq[(size_t)items[k]]); }
+        for (int k = lo; k < hi; ++k) box_merge(n.box, cull[(size_t)items[k]]);
         if (hi - lo == 1) {
             n.prim = items[lo];
             set(me, n);
@@ -388,7 +386,7 @@ struct SahBuilder {
 };
 
 // Collapses the binary tree to <= 4 children per node and writes the wide nodes breadth-first.
-void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root) {
+void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root, const std::vector<Box>& cull, const std::vector<float>& cq) {
     struct Item { int up, wide, level, sp; };
     std::vector<Item> queue;
     queue.reserve(up.size() / 2 + 2);
@@ -425,19 +423,24 @@ void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root) {
         s.dwide.resize((size_t)first + ni, empty_wide());
         DWide w = empty_wide();
         uint32_t meta = 0;
+        float qmax = 0.0f;
         for (int k = 0; k < n; ++k) {
             const UpNode& c = up[(size_t)slots[k]];
-            set_child_box(w, k, c.box);
             meta |= 1u << k;
             if (c.left < 0) {
+                // a primitive child carries its own (tight) culling box; Q of the node = the largest of its spheres
                 const HostPrim& p = s.prims[(size_t)s.order[(size_t)c.prim]];
+                set_child_box(w, k, cull[(size_t)c.prim]);
                 meta |= (16u << k) | ((uint32_t)p.type << (16 + 2 * k));
                 w.f[27 + k] = bits_f((uint32_t)c.prim);
+                qmax = std::max(qmax, cq[(size_t)c.prim]);
+            } else {
+                set_child_box(w, k, c.box);
             }
         }
         w.f[24] = bits_f((uint32_t)first);
         w.f[25] = bits_f(meta);
-        w.f[26] = u.q;
+        w.f[26] = qmax;
         s.dwide[(size_t)it.wide] = w;
         // the traversal pushes up to ni - 1 sibling nodes before it descends: the stack a ray can need below here
         s.stack_need = std::max(s.stack_need, it.sp + std::max(0, ni - 1) + 1);
@@ -496,31 +499,38 @@ void flatten_scene(HostScene& s) {
                 g += std::max(std::fabs((double)s.tree[0].box.lo[a]), std::fabs((double)s.tree[0].box.hi[a]));
             if (g < 1e30) scene_g = std::max(scene_g, g);
         }
-        // culling box + sphere coefficient of every primitive (sorted order). A primitive whose culling box
-        // cannot be bounded (degenerate quads, cull_pad) takes the box of its reference leaf instead: it is only
-        // ever tested when that box passes.
-        std::vector<Box> cull((size_t)n);
+        // Per primitive (sorted order):
+        //   cull[k], cq[k] : its culling box + sphere coefficient -- what the node that holds it tests;
+        //   abox[k]        : what its ANCESTORS must contain. A shape is only ever tested when its reference leaf's
+        //                    box passes the reference's test (the gate), so every ray that matters passes that box:
+        //                    the culling box, or -- where the culling box is unbounded (degenerate quads) or needs
+        //                    the distance-dependent sphere term Q, which must not leak into every level of the
+        //                    tree -- the (padded) box of the reference leaf.
+        std::vector<Box> cull((size_t)n), abox((size_t)n);
         std::vector<float> cq((size_t)n, 0.0f);
         parallel_chunks((size_t)n, 8192, [&](size_t k_lo, size_t k_hi) {
             for (size_t k = k_lo; k < k_hi; ++k) {
                 const HostPrim& p = s.prims[(size_t)s.order[k]];
                 double pad = 0.0;
                 float q = 0.0f;
-                Box cb;
+                Box cb, lb;
+                const F4 lo = s.dleafbox[2 * k], hi = s.dleafbox[2 * k + 1];
+                const float l3[3] = {lo.x, lo.y, lo.z}, h3[3] = {hi.x, hi.y, hi.z};
+                for (int a = 0; a < 3; ++a) {
+                    const double m = 1e-6 * (std::fabs((double)l3[a]) + std::fabs((double)h3[a])) + 1e-6;
+                    lb.lo[a] = std::nextafter((float)((double)l3[a] - m), -FLT_MAX);
+                    lb.hi[a] = std::nextafter((float)((double)h3[a] + m), FLT_MAX);
+                }
                 if (cull_pad(p, scene_g, pad, q)) {
                     for (int a = 0; a < 3; ++a) {
                         cb.lo[a] = std::nextafter((float)((double)p.box.lo[a] - pad), -FLT_MAX);
                         cb.hi[a] = std::nextafter((float)((double)p.box.hi[a] + pad), FLT_MAX);
                     }
+                    abox[k] = q > 0.0f ? lb : cb;
                 } else {
-                    const F4 lo = s.dleafbox[2 * k], hi = s.dleafbox[2 * k + 1];
-                    const float l3[3] = {lo.x, lo.y, lo.z}, h3[3] = {hi.x, hi.y, hi.z};
-                    for (int a = 0; a < 3; ++a) {
-                        const double m = 1e-6 * (std::fabs((double)l3[a]) + std::fabs((double)h3[a])) + 1e-6;
-                        cb.lo[a] = std::nextafter((float)((double)l3[a] - m), -FLT_MAX);
-                        cb.hi[a] = std::nextafter((float)((double)h3[a] + m), FLT_MAX);
-                    }
+                    cb = lb;
                     q = 0.0f;
+                    abox[k] = lb;
                 }
                 cull[k] = cb;
                 cq[k] = q;
@@ -529,12 +539,12 @@ void flatten_scene(HostScene& s) {
         // the traversal stacks live in shared memory (36 entries x 6 blocks is what an SM holds): a tree that could
         // need more is rebuilt with a balance bound
         for (double min_frac : {0.0, 0.2, 0.35, 0.5}) {
-            SahBuilder b{cull, cq, min_frac, {}, {}};
+            SahBuilder b{abox, min_frac, {}, {}};
             b.items.resize((size_t)n);
             for (int k = 0; k < n; ++k) b.items[(size_t)k] = k;
             b.nodes.resize(2 * (size_t)n);
             const int root = b.build(0, n, 6);
-            emit_wide_tree(s, b.nodes, root);
+            emit_wide_tree(s, b.nodes, root, cull, cq);
             if (std::getenv("RT_B200_DEBUG")) std::fprintf(stderr, "[rt_b200] device tree: min_frac %.2f -> %zu nodes, depth %d, stack need %d\n", min_frac, s.dwide.size(), s.wide_depth, s.stack_need);
             if (s.stack_need <= 36) break;
         }
