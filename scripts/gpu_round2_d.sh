@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+OUT=gpurun_out/r2d_ab.jsonl; : > $OUT
+( time timeout 1200 python -m pytest tests -m gpu -x -q ) > gpurun_out/r2d_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/r2d_pytest.log
+V=$PWD/ray_tracying_b200/variants
+run() { env "$@" 2>>gpurun_out/r2d_err.log | tail -1 >> $OUT; }
+for wl in mixed100k soup1m glossy250k dof4m; do
+  steps=6; [ $wl != mixed100k ] && steps=3; [ $wl = dof4m ] && steps=1
+  run python scripts/perf_probe.py $wl $steps new
+  run RT_B200_LIB=$V/librt_b200_mb7.so python scripts/perf_probe.py $wl $steps mb7
+  run RT_B200_LIB=$V/librt_b200_r2leaves.so python scripts/perf_probe.py $wl $steps r2leaves
+done
+tail -4 gpurun_out/r2d_pytest.log; cat $OUT
