@@ -63,7 +63,7 @@ namespace rtb {
 #define RT_TRACE_THREADS 128
 #endif
 #ifndef RT_TRACE_MINBLOCKS
-#define RT_TRACE_MINBLOCKS 6
+#define RT_TRACE_MINBLOCKS 7  /* 72 registers: measured +2-3 % over 6 blocks / 80 registers on configs[1]-[3] (profiles/README.md) */
 #endif
 #ifndef RT_ANY_SORTED_PACKET
 #define RT_ANY_SORTED_PACKET 0
