@@ -401,8 +401,9 @@ def run_ours(args, wl):
             return {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "Gbox-tests/s", "frac": achieved / peak,
                     "traffic": cap["dram_bytes_per_launch"] if cap else None,
                     "traffic_source": (captured.get("source") if cap else "no ncu capture of these kernel sources under profiles/"),
-                    "peak_source": "rt_traversal_peak measured in this run: trav_step (4 slab tests, sort, push/pop) with converged warps on "
-                                   "64 L1-resident nodes; closest-hit %.1f / any-hit %.1f Gbox-tests/s" % (leg["peak_closest"] / 1e9, leg["peak_any"] / 1e9),
+                    "peak_source": "rt_traversal_peak measured in this run: the loop's node step (4 slab tests, sorting network, 3 pushes, "
+                                   "descent = full work) with converged warps on 64 L1-resident synthetic nodes; closest-hit %.1f / any-hit "
+                                   "%.1f Gbox-tests/s" % (leg["peak_closest"] / 1e9, leg["peak_any"] / 1e9),
                     "kernel": "traversal loops: trace_packet_kernel + trace_kernel + shadow_packet_kernel + shadow_kernel",
                     "launches_per_step": leg["n_trav_launches"], "avg_launch_ms": leg["trav_ms"] / max(1, leg["n_trav_launches"]),
                     "box_tests_per_launch": leg["my_box_tests"] // max(1, leg["n_trav_launches"]),

@@ -255,10 +255,12 @@ int rt_render_multi(rt_scene* scene, const rt_render_params* p, int32_t n_device
 int rt_scene_launch_count(rt_scene* scene, uint64_t* launches);
 
 /* Measured ceiling of the traversal loop on the current device (the denominator of bench.py's
- * roofline): the loop's own node step -- four conservative slab tests, sort, push / pop on the
- * shared-memory stack -- run by fully converged warps over the top n_nodes inner nodes of this scene's
- * tree (L1-resident), `steps` node visits per thread, best of `repeats` launches. any_hit selects the
- * occlusion-query flavour (shadow kernels) or the closest-hit one. Returns box tests per second. */
+ * roofline): the loop's own node step -- four conservative slab tests, the sorting network, push / pop
+ * on the shared-memory stack -- run by fully converged warps over n_nodes SYNTHETIC nodes (L1-resident)
+ * whose four children all contain the scene, so that every step does its full work (four passes, three
+ * pushes, one descent); `steps` node visits per thread, best of `repeats` launches. any_hit selects the
+ * occlusion-query flavour (shadow kernels) or the closest-hit one. Returns box tests per second: what
+ * the traversal kernels would reach with no divergence, no cache misses, no fetch / primitive phases. */
 int rt_traversal_peak(rt_scene* scene, int32_t any_hit, int32_t n_nodes, int32_t steps, int32_t repeats,
                       double* box_tests_per_s, float* ms);
 

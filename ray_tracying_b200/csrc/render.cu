@@ -1988,9 +1988,9 @@ static int render_multi(HostScene& h, const rt_render_params& rp_in, int n_devic
 
 // ---------------------------------------------------------------------------------------------
 // Traversal ceiling: trav_step -- the very code of the traversal loop -- with all 32 lanes of every
-// warp busy on nodes that stay in L1 (the top `n_nodes` nodes of the scene's own tree, visited round
-// robin; the stack is reset after every step). Box tests per second of that loop on this chip is
-// what the traversal kernels would reach without divergence, cache misses, fetch / primitive
+// warp busy on nodes that stay in L1 (`n_nodes` synthetic nodes whose children all contain the scene,
+// visited round robin; the stack is reset after every step). Box tests per second of that loop on this
+// chip is what the traversal kernels would reach without divergence, cache misses, fetch / primitive
 // phases: the denominator of bench.py's roofline.
 // ---------------------------------------------------------------------------------------------
 template <bool ANY>
@@ -2169,13 +2169,37 @@ int rt_traversal_peak(rt_scene* scene, int32_t any_hit, int32_t n_nodes, int32_t
     std::memset(&b, 0, sizeof(b));
     b.prims = ds->prims; b.wide = ds->wide; b.leafbox = ds->leafbox; b.n_prims = (int)h.dprims.size(); b.use_bvh = 1; b.prune = 1;
     b.stack_depth = ds->stack_depth;
-    // nodes with node children only (primitive children are parked in `pend` instead of pushed): the first n
-    // nodes in breadth-first order are the top of the tree
-    int n = 0;
-    const int limit = std::min<int>(n_nodes, (int)h.dwide.size());
-    while (n < limit && ((((const uint32_t*)h.dwide[n].f)[25] >> 4) & 15u) == 0u) ++n;
-    if (n < 1) n = 1;
+    // FULL-WORK steps on synthetic nodes: every node has four node children whose boxes all contain the scene, so
+    // every ray passes all four -- four slab tests, the whole sorting network, three pushes, one descent: every
+    // instruction of the step does work, which no real traversal exceeds per box test. (The top of a real tree would
+    // make the number depend on the scene: steps whose children all miss skip the pushes warp-wide.)
+    const int n = std::max(4, std::min(n_nodes, 4096));
     const rtb::Box& box = h.tree[0].box;
+    std::vector<rtb::DWide> synth((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        rtb::DWide w;
+        for (float& x : w.f) x = 0.0f;
+        for (int k = 0; k < 4; ++k) {
+            for (int a = 0; a < 3; ++a) {
+                const float ext = box.hi[a] - box.lo[a];
+                w.f[8 * a + k] = box.lo[a] - (1.0f + 0.25f * k) * ext - 1.0f;      // lo: slightly different entry distances per child
+                w.f[8 * a + 4 + k] = box.hi[a] + (1.0f + 0.25f * k) * ext + 1.0f;  // hi
+            }
+        }
+        const uint32_t first = (uint32_t)((i * 4 + 1) % (n - 3)), meta = 0xFu;
+        std::memcpy(&w.f[24], &first, 4);
+        std::memcpy(&w.f[25], &meta, 4);
+        synth[(size_t)i] = w;
+    }
+    float* d_synth = nullptr;
+    if (cudaMalloc((void**)&d_synth, synth.size() * sizeof(rtb::DWide)) != cudaSuccess ||
+        cudaMemcpy(d_synth, synth.data(), synth.size() * sizeof(rtb::DWide), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(d_synth);
+        rtb::set_error("rt_traversal_peak: cudaMalloc / cudaMemcpy failed");
+        return RT_ERR_CUDA;
+    }
+    b.wide = d_synth;
     const float3 eye = make_float3(h.cam.location[0], h.cam.location[1], h.cam.location[2]);
     const float3 lo = make_float3(box.lo[0], box.lo[1], box.lo[2]), hi = make_float3(box.hi[0], box.hi[1], box.hi[2]);
     unsigned long long* d = nullptr;
@@ -2208,6 +2232,7 @@ int rt_traversal_peak(rt_scene* scene, int32_t any_hit, int32_t n_nodes, int32_t
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     cudaFree(d);
+    cudaFree(d_synth);
     return rc;
 }
 
