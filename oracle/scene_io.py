@@ -73,7 +73,10 @@ class _Tables:
     def material(self, mj):
         if mj is not None and id(mj) in self.by_identity:
             return self.by_identity[id(mj)][1]
-        idx = self._material(mj)
+        try:
+            idx = self._material(mj)
+        except (KeyError, ValueError, TypeError):  # json_loader.cpp:91-95: a material that fails to parse is the default one
+            idx = self._material(None)
         if mj is not None:
             self.by_identity[id(mj)] = (mj, idx)  # keeps mj alive, so the id stays unique
         return idx

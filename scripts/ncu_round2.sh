@@ -12,3 +12,10 @@ ncu --set full --clock-control none --import-source on -k regex:'trace_kernel|sh
 $P soup1m 1 > gpurun_out/ncu_plain3.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'shadow_packet_kernel|trace_packet_kernel' -s 40 -c 2 -o gpurun_out/prof_r2_soup1m $P soup1m 1 > gpurun_out/ncu_f2.log 2>&1
 ls -la gpurun_out/*.ncu-rep
+# 4. the shared-memory staging A/B (RT_STAGE_TOP=21 build): the per-ray kernels of level 1, to set L1 hit rate and
+#    long_scoreboard against the default build's (capture 2)
+export RT_B200_LIB=$PWD/ray_tracying_b200/variants/librt_b200_stage21.so
+$P mixed100k 1 > gpurun_out/ncu_plain4.log 2>&1 &&
+ncu --set full --clock-control none -k regex:'trace_kernel|shadow_kernel' -s 10 -c 2 -o gpurun_out/prof_r2_mixed100k_stage21 $P mixed100k 1 > gpurun_out/ncu_f4.log 2>&1
+unset RT_B200_LIB
+ls -la gpurun_out/*.ncu-rep

@@ -114,6 +114,53 @@ def test_missing_file_and_bad_json_report_errors(rt, tmp_path):
         rt.Scene.from_json(str(nocam))
 
 
+def test_parallel_loader_builds_the_scene_a_serial_loader_builds(rt, tmp_path):
+    """The four shape arrays are parsed and converted element by element on several threads; materials, textures and
+    the primitives' order are settled serially in element order. 30k shapes (enough for several chunks) with
+    invalid entries sprinkled in: the scene (shape order after BVH construction, tree, counts) is identical with one
+    host thread and with many, and identical to the oracle's independent Python loader + C++ builder."""
+    from ray_tracying_b200 import scenes
+    sc = scenes.mixed_scene(30000, seed=5, resolution=(64, 36), texture_file="checker.jpg")
+    sc["planes"][100:100] = [{"corners": [[0, 0, 0]]}, 7, {"corners": "x"}]
+    sc["spheres"][50:50] = [{"rotation": [0, 0, 0]}, {"location": [0, 0, 0], "material": {"diffuse_color": [1, 2]}}]
+    sc["cubes"][10:10] = [{"rotation": [0, 0, 0]}]
+    path = scene_file(tmp_path, sc)
+    code = ("import sys, json; sys.path.insert(0, %r)\n"
+            "import numpy as np, ray_tracying_b200 as rt\n"
+            "s = rt.Scene.from_json(%r, %r)\n"
+            "np.save(%r + sys.argv[1] + '.npy', s.shape_order()); print(json.dumps(s.counts()))\n") % (ROOT, path, GOLDEN, str(tmp_path / "order_"))
+    outs = {}
+    for threads in ("1", "7"):
+        r = subprocess.run([os.sys.executable, "-c", code, threads], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                           env=dict(os.environ, RT_B200_HOST_THREADS=threads), timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[threads] = (json.loads(r.stdout.strip().splitlines()[-1]), np.load(str(tmp_path / ("order_" + threads + ".npy"))), r.stderr)
+    assert outs["1"][0] == outs["7"][0] and np.array_equal(outs["1"][1], outs["7"][1])
+    assert outs["1"][2] == outs["7"][2], "warnings come out in element order whatever the thread count"
+    assert outs["1"][0]["shapes"] == 30001 and "Skipping invalid plane definition" in outs["1"][2]  # the sphere with a bad material keeps the default material
+    from oracle import oracle, scene_io
+    o = oracle.OracleScene(*scene_io.scene_arrays(sc, GOLDEN))
+    assert np.array_equal(o.shape_order(), outs["7"][1])
+
+
+def test_malformed_element_rejects_the_whole_document(rt, tmp_path):
+    """A syntax error inside a shape array (whose elements are parsed on their own, later) still fails the load,
+    like one parse of the whole document would; a duplicate key keeps its LAST value, arrays included."""
+    d = golden_scene("few_3")
+    text = json.dumps(d)
+    key = '"planes": [' if '"planes": [' in text else '"spheres": ['
+    bad = tmp_path / "bad_elem.json"
+    bad.write_text(text.replace(key, key + '{"corners": [[0,0,0],[1,0,0],[1,1,0],[0,1,x]]}, ', 1))
+    with pytest.raises(rt.RtError) as e:
+        rt.Scene.from_json(str(bad), GOLDEN)
+    assert e.value.status == -2
+    n0 = rt.Scene.from_json(scene_file(tmp_path, d), GOLDEN).counts()["shapes"]
+    dup = tmp_path / "dup.json"
+    dup.write_text(text[:-1] + ', "spheres": [], "cubes": 3}')
+    n1 = rt.Scene.from_json(str(dup), GOLDEN).counts()["shapes"]
+    assert n1 == n0 - len(d.get("spheres", [])) - len(d.get("cubes", []))
+
+
 def test_ppm_roundtrip_and_reference_format(rt, tmp_path):
     rng = np.random.default_rng(0)
     img = rng.integers(0, 256, (5, 7, 3), dtype=np.uint8)
