@@ -65,6 +65,9 @@ namespace rtb {
 #ifndef RT_TRACE_MINBLOCKS
 #define RT_TRACE_MINBLOCKS 7  /* 72 registers: measured +2-3 % over 6 blocks / 80 registers on configs[1]-[3] (profiles/README.md) */
 #endif
+#ifndef RT_WAVE_MINBLOCKS
+#define RT_WAVE_MINBLOCKS RT_TRACE_MINBLOCKS  /* resident blocks per SM of the per-ray kernels (trace_kernel, shadow_kernel) */
+#endif
 #ifndef RT_ANY_SORTED_PACKET
 #define RT_ANY_SORTED_PACKET 0
 #endif
@@ -318,6 +321,21 @@ RT_DEV void wave_loop(const BvhView& bvh, Src& src, unsigned int* counter, unsig
             }
         }
         const bool has_pend = s.pend != 0u;
+#if RT_PEND_SLOTS == 2
+        // a lane may step past ONE node with candidates: it only has to stop when both slots are taken (or it has no
+        // node left); the primitive phase runs when at least as many lanes are stopped by it as can step
+        const bool full = (s.pend & 15u) != 0u && (s.pend & 240u) != 0u;
+        const bool can_step = item >= 0 && !full && s.cur != RT_CUR_NONE;
+        const bool blocked = has_pend && !can_step;
+        const unsigned int pm = __ballot_sync(FULL, blocked), sm = __ballot_sync(FULL, can_step);
+        const bool do_prims = pm != 0u && (sm == 0u || __popc(pm) >= __popc(sm));
+        if (do_prims) trav_prims<ANY, STATS>(bvh, s, st);
+        else if (can_step) {
+#pragma unroll 1
+            for (int k = 0; k < RT_STEPS_PER_VOTE && !((s.pend & 15u) != 0u && (s.pend & 240u) != 0u) && s.cur != RT_CUR_NONE; ++k)
+                trav_step<ANY, STATS>(bvh, s, stride, st);
+        }
+#else
         const bool can_step = item >= 0 && !has_pend && s.cur != RT_CUR_NONE;
         const unsigned int pm = __ballot_sync(FULL, has_pend), sm = __ballot_sync(FULL, can_step);
         const bool do_prims = pm != 0u && (sm == 0u || (RT_PHASE_MAJORITY ? __popc(pm) >= __popc(sm) : __popc(pm) >= RT_T_PRIM));
@@ -327,6 +345,7 @@ RT_DEV void wave_loop(const BvhView& bvh, Src& src, unsigned int* counter, unsig
             for (int k = 0; k < RT_STEPS_PER_VOTE && s.pend == 0u && s.cur != RT_CUR_NONE; ++k)
                 trav_step<ANY, STATS>(bvh, s, stride, st);
         }
+#endif
         if (item >= 0 && s.pend == 0u && s.cur == RT_CUR_NONE) { src.store(item, s); item = -1; }
     }
 }
@@ -527,7 +546,7 @@ struct ViewRays {
 };
 
 template <bool STATS>
-__global__ void __launch_bounds__(RT_TRACE_THREADS, RT_TRACE_MINBLOCKS) trace_kernel(const __grid_constant__ FrameParams p, int level) {
+__global__ void __launch_bounds__(RT_TRACE_THREADS, RT_WAVE_MINBLOCKS) trace_kernel(const __grid_constant__ FrameParams p, int level) {
     unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
     const unsigned int n = min(lv[L_RAYS], (unsigned int)p.capacity);
     TraceStats st = {0u, 0u};
@@ -824,7 +843,7 @@ typedef ShadowRaysT<false> ShadowRays;
 typedef ShadowRaysT<RT_SELF_OCCLUSION != 0> ShadowRaysPacket;
 
 template <bool STATS>
-__global__ void __launch_bounds__(RT_TRACE_THREADS, RT_TRACE_MINBLOCKS) shadow_kernel(const __grid_constant__ FrameParams p, int level) {
+__global__ void __launch_bounds__(RT_TRACE_THREADS, RT_WAVE_MINBLOCKS) shadow_kernel(const __grid_constant__ FrameParams p, int level) {
     unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
     const unsigned long long n = (unsigned long long)lv[L_RECS] * (unsigned long long)p.shadow_per_rec;
     TraceStats st = {0u, 0u};
@@ -1126,7 +1145,8 @@ struct DeviceScene {
     long long batch_slots = [] { const char* e = std::getenv("RT_B200_BATCH_SLOTS"); return e ? std::atoll(e) : (8ll << 20); }();
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     int sm_count = 0;
-    int trace_blocks = 1, shadow_blocks = 1;  // resident blocks per SM
+    int trace_blocks = 1, shadow_blocks = 1;  // resident blocks per SM: per-ray kernels ...
+    int trace_packet_blocks = 1, shadow_packet_blocks = 1;  // ... and packet kernels (their stacks are per warp: less shared memory)
     int stack_depth = 4;         // entries per thread of the per-ray kernels' stacks
     int packet_stack_depth = 4;  // entries per warp of the packet kernels' stacks
     int n_staged = 0;            // RT_STAGE_TOP builds: top nodes staged in shared memory by the per-ray kernels
@@ -1306,8 +1326,13 @@ static int device_scene(HostScene& h, DeviceScene** out) {
         }
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_blocks, trace_kernel<false>, RT_TRACE_THREADS, d->stack_bytes));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->shadow_blocks, shadow_kernel<false>, RT_TRACE_THREADS, d->stack_bytes));
+        const size_t packet_smem0 = (size_t)(RT_TRACE_THREADS / 32) * d->packet_stack_depth * 16;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_packet_blocks, trace_packet_kernel<false>, RT_TRACE_THREADS, packet_smem0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->shadow_packet_blocks, shadow_packet_kernel<false>, RT_TRACE_THREADS, packet_smem0));
         d->trace_blocks = std::max(1, d->trace_blocks);
         d->shadow_blocks = std::max(1, d->shadow_blocks);
+        d->trace_packet_blocks = std::max(1, d->trace_packet_blocks);
+        d->shadow_packet_blocks = std::max(1, d->shadow_packet_blocks);
         return RT_OK;
     };
     rc = init();
@@ -1518,14 +1543,14 @@ static int enqueue_frame(const HostScene& h, DeviceScene* d, FrameParams& k, boo
     for (int i = 0; i < 2; ++i) { k.recs[i] = d->recs[i]; k.vis[i] = d->vis[i]; }
     k.accum = d->accum; k.lvl = d->lvl; k.totals = d->totals;
     k.overflow_host = d->overflow_host;
-    const int grid_trace = d->sm_count * d->trace_blocks;
-    const int grid_shadow = d->sm_count * d->shadow_blocks;
+    const int grid_trace = d->sm_count * d->trace_blocks, grid_trace_packet = d->sm_count * d->trace_packet_blocks;
+    const int grid_shadow = d->sm_count * d->shadow_blocks, grid_shadow_packet = d->sm_count * d->shadow_packet_blocks;
     const int grid_wide = d->sm_count * 8;
     // ... and at deeper levels, where the record count can grow up to the queue capacity, keep
     // capacity x (shadow rays per hit) + (what the persistent warps over-fetch past the end) below
     // 2^32. All of the allocated queue space otherwise, also after a retry with smaller batches (the
     // allocation never shrinks, so halving the batch really halves the pressure on the queues).
-    const long long overshoot = (long long)std::max(grid_trace, grid_shadow) * (RT_TRACE_THREADS / 32) * 128 + 65536;
+    const long long overshoot = (long long)std::max(std::max(grid_trace, grid_shadow), std::max(grid_trace_packet, grid_shadow_packet)) * (RT_TRACE_THREADS / 32) * 128 + 65536;
     const long long work_cap = ((1ll << 32) - overshoot) / spr;
     k.capacity = (int)std::min<long long>(std::min<long long>(d->capacity, (1ll << 30)), work_cap);
 
@@ -1594,8 +1619,8 @@ static int enqueue_frame(const HostScene& h, DeviceScene* d, FrameParams& k, boo
                 if (collect) trace_literal_kernel<true><<<grid_wide, 128, 0, stream>>>(k, level);
                 else trace_literal_kernel<false><<<grid_wide, 128, 0, stream>>>(k, level);
             } else if (packets) {
-                if (collect) trace_packet_kernel<true><<<grid_trace, RT_TRACE_THREADS, packet_smem, stream>>>(k, level);
-                else trace_packet_kernel<false><<<grid_trace, RT_TRACE_THREADS, packet_smem, stream>>>(k, level);
+                if (collect) trace_packet_kernel<true><<<grid_trace_packet, RT_TRACE_THREADS, packet_smem, stream>>>(k, level);
+                else trace_packet_kernel<false><<<grid_trace_packet, RT_TRACE_THREADS, packet_smem, stream>>>(k, level);
             } else {
                 if (collect) trace_kernel<true><<<grid_trace, RT_TRACE_THREADS, d->stack_bytes, stream>>>(k, level);
                 else trace_kernel<false><<<grid_trace, RT_TRACE_THREADS, d->stack_bytes, stream>>>(k, level);
@@ -1616,8 +1641,8 @@ static int enqueue_frame(const HostScene& h, DeviceScene* d, FrameParams& k, boo
                     if (collect) shadow_literal_kernel<true><<<grid_wide, 128, 0, aux>>>(k, level);
                     else shadow_literal_kernel<false><<<grid_wide, 128, 0, aux>>>(k, level);
                 } else if (shadow_packets) {
-                    if (collect) shadow_packet_kernel<true><<<grid_shadow, RT_TRACE_THREADS, packet_smem, aux>>>(k, level);
-                    else shadow_packet_kernel<false><<<grid_shadow, RT_TRACE_THREADS, packet_smem, aux>>>(k, level);
+                    if (collect) shadow_packet_kernel<true><<<grid_shadow_packet, RT_TRACE_THREADS, packet_smem, aux>>>(k, level);
+                    else shadow_packet_kernel<false><<<grid_shadow_packet, RT_TRACE_THREADS, packet_smem, aux>>>(k, level);
                 } else {
                     if (collect) shadow_kernel<true><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, aux>>>(k, level);
                     else shadow_kernel<false><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, aux>>>(k, level);

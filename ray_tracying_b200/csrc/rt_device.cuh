@@ -494,7 +494,8 @@ struct TravState {
     unsigned int sp0;  // ... of entry 0 (stack empty when sp == sp0)
     unsigned int sp_end;  // RT_CHECKS: address one past the last entry
     unsigned int pend; // bit k: child k of node pend_node is a primitive waiting for its test
-    int pend_node;
+    int pend_node;     //        (RT_PEND_SLOTS == 2: bits 4-7 belong to pend_node2 -- a lane may keep stepping
+    int pend_node2;    //        past one node with candidates before the warp's primitive phase has run)
     unsigned int staged;  // RT_STAGE_TOP: shared-space address of the staged top nodes
 };
 
@@ -509,6 +510,7 @@ RT_DEV bool trav_begin(const BvhView& b, TravState& s, const Ray& r, float max_t
     s.cur = RT_CUR_NONE;
     s.pend = 0u;
     s.pend_node = 0;
+    s.pend_node2 = 0;
     if (b.n_prims == 0) return true;
     const float BIG = 1e30f;
     s.ix = 1.0f / r.dx; s.iy = 1.0f / r.dy; s.iz = 1.0f / r.dz;
@@ -551,6 +553,9 @@ RT_DEV void wide_child_test(const TravState& s, float lox, float hix, float loy,
     surely = m >= sl + s.KS;
 }
 
+#ifndef RT_PEND_SLOTS
+#define RT_PEND_SLOTS 1
+#endif
 // Visits node s.cur: tests its (up to) four children. Node children are pushed far-to-near and
 // the nearest becomes s.cur; primitive children whose culling box passes become s.pend. The
 // caller guarantees s.cur != RT_CUR_NONE and s.pend == 0. `stride` = bytes between two stack entries
@@ -585,8 +590,18 @@ RT_DEV void trav_step(const BvhView& b, TravState& s, unsigned int stride, Trace
     int next = RT_CUR_NONE;
     unsigned int sp = s.sp;
     // primitive children whose culling box passes wait for the warp's next primitive phase
+#if RT_PEND_SLOTS == 2
+    {
+        const unsigned int cand = pm & (meta >> 4) & 15u;
+        if (cand != 0u) {
+            if ((s.pend & 15u) == 0u) { s.pend |= cand; s.pend_node = node; }
+            else { s.pend |= cand << 4; s.pend_node2 = node; }
+        }
+    }
+#else
     s.pend = pm & (meta >> 4);
     s.pend_node = node;
+#endif
     pm &= ~(meta >> 4);
     if (ANY && !RT_ANY_SORTED) {
         // occlusion query: order does not matter
@@ -654,53 +669,58 @@ RT_DEV bool gate_passes(const BvhView& b, const TravState& s, int idx) {
 // warp run the same intersection routine together. MUST be called by all 32 lanes.
 template <bool ANY, bool STATS>
 RT_DEV void trav_prims(const BvhView& b, TravState& s, TraceStats& st) {
-    unsigned int m_x = 0u, m_p = 0u;
-    const float* w = b.wide + (size_t)s.pend_node * 32;
-    if (s.pend != 0u) {
-        const unsigned int t = __float_as_uint(__ldg(w + 25)) >> 16;  // 2 bits of type per child
-        const unsigned int pl = ((t & 3u) == 3u ? 1u : 0u) | (((t >> 2) & 3u) == 3u ? 2u : 0u) | (((t >> 4) & 3u) == 3u ? 4u : 0u) |
-                                (((t >> 6) & 3u) == 3u ? 8u : 0u);
-        m_p = s.pend & pl;
-        m_x = s.pend & ~pl;
-        s.pend = 0u;
-    }
     bool occluded = false;
-    while (__any_sync(0xffffffffu, m_x != 0u)) {
-        if (m_x != 0u) {
-            const int k = __ffs(m_x) - 1;
-            m_x &= m_x - 1u;
-            const int idx = __float_as_int(__ldg(w + 27 + k));
-            Hit h;
-            if (gate_passes(b, s, idx)) {
-                if (STATS) st.prims++;
-                if (intersect_prim<false, PRIM_XFORM>(b.prims, idx, s.r, h)) {
-                    if (ANY) {
-                        if (!(h.t > s.max_t)) { occluded = true; m_x = 0u; m_p = 0u; }
-                    } else if (h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) {
-                        s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
+#pragma unroll 1
+    for (int slot = 0; slot < RT_PEND_SLOTS; ++slot) {
+        unsigned int m_x = 0u, m_p = 0u;
+        const unsigned int mine = RT_PEND_SLOTS == 2 ? ((s.pend >> (4 * slot)) & 15u) : s.pend;
+        const float* w = b.wide + (size_t)((RT_PEND_SLOTS == 2 && slot == 1) ? s.pend_node2 : s.pend_node) * 32;
+        if (mine != 0u && !occluded) {
+            const unsigned int t = __float_as_uint(__ldg(w + 25)) >> 16;  // 2 bits of type per child
+            const unsigned int pl = ((t & 3u) == 3u ? 1u : 0u) | (((t >> 2) & 3u) == 3u ? 2u : 0u) | (((t >> 4) & 3u) == 3u ? 4u : 0u) |
+                                    (((t >> 6) & 3u) == 3u ? 8u : 0u);
+            m_p = mine & pl;
+            m_x = mine & ~pl;
+        }
+        if (RT_PEND_SLOTS == 2 && !__any_sync(0xffffffffu, (m_x | m_p) != 0u)) continue;
+        while (__any_sync(0xffffffffu, m_x != 0u)) {
+            if (m_x != 0u) {
+                const int k = __ffs(m_x) - 1;
+                m_x &= m_x - 1u;
+                const int idx = __float_as_int(__ldg(w + 27 + k));
+                Hit h;
+                if (gate_passes(b, s, idx)) {
+                    if (STATS) st.prims++;
+                    if (intersect_prim<false, PRIM_XFORM>(b.prims, idx, s.r, h)) {
+                        if (ANY) {
+                            if (!(h.t > s.max_t)) { occluded = true; m_x = 0u; m_p = 0u; }
+                        } else if (h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) {
+                            s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
+                        }
+                    }
+                }
+            }
+        }
+        while (__any_sync(0xffffffffu, m_p != 0u)) {
+            if (m_p != 0u) {
+                const int k = __ffs(m_p) - 1;
+                m_p &= m_p - 1u;
+                const int idx = __float_as_int(__ldg(w + 27 + k));
+                Hit h;
+                if (gate_passes(b, s, idx)) {
+                    if (STATS) st.prims++;
+                    if (intersect_prim<false, PRIM_PLANE>(b.prims, idx, s.r, h)) {
+                        if (ANY) {
+                            if (!(h.t > s.max_t)) { occluded = true; m_p = 0u; }
+                        } else if (h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) {
+                            s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
+                        }
                     }
                 }
             }
         }
     }
-    while (__any_sync(0xffffffffu, m_p != 0u)) {
-        if (m_p != 0u) {
-            const int k = __ffs(m_p) - 1;
-            m_p &= m_p - 1u;
-            const int idx = __float_as_int(__ldg(w + 27 + k));
-            Hit h;
-            if (gate_passes(b, s, idx)) {
-                if (STATS) st.prims++;
-                if (intersect_prim<false, PRIM_PLANE>(b.prims, idx, s.r, h)) {
-                    if (ANY) {
-                        if (!(h.t > s.max_t)) { occluded = true; m_p = 0u; }
-                    } else if (h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) {
-                        s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
-                    }
-                }
-            }
-        }
-    }
+    s.pend = 0u;
     if (ANY && occluded) { s.best_prim = 0; s.cur = RT_CUR_NONE; s.sp = s.sp0; }
 }
 
