@@ -108,6 +108,7 @@ struct FrameParams {
     const int* __restrict__ tiles;
     const int* __restrict__ tile_slot;
     int win_x0, win_y0, win_x1, win_y1;  // only pixels inside this window are rendered (whole frame by default)
+    int sort_emit;  // 1: shade_kernel orders the rays it emits by direction octant within its 256-ray runs
     int packed;  // 1: outputs are indexed tile-major over this rank's tiles (rt_render_multi) instead of frame row-major
     // wavefront buffers
     float4* q[2];                  // ray queues (ping-pong by level parity), 3 x float4 per ray
@@ -183,6 +184,44 @@ RT_DEV void block_reserve2(unsigned int* counter, bool want1, bool want2, unsign
     slot2 = base + sh[8 + warp] + (unsigned int)__popc(m2 & lt);
     __syncthreads();  // sh is reused by the next call
 }
+
+// Keyed version: the block's slots are ordered by (class, key, thread) -- class 1 before class 2, keys 0..7 within a
+// class -- so that rays with the same key (direction octant) sit next to each other in the queue and end up in the
+// same warps of the next level's traversal. `sh` = 132 words of shared memory. MUST be called by all threads of a
+// 256-thread block.
+RT_DEV void block_reserve_keyed(unsigned int* counter, bool want1, int key1, bool want2, int key2, unsigned int* sh,
+                                unsigned int& slot1, unsigned int& slot2) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int lt = (1u << lane) - 1u;
+    unsigned int rank1 = 0, rank2 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const unsigned int m1 = __ballot_sync(0xffffffffu, want1 && key1 == k), m2 = __ballot_sync(0xffffffffu, want2 && key2 == k);
+        if (lane == 0) { sh[k * 8 + warp] = (unsigned int)__popc(m1); sh[64 + k * 8 + warp] = (unsigned int)__popc(m2); }
+        if (want1 && key1 == k) rank1 = (unsigned int)__popc(m1 & lt);
+        if (want2 && key2 == k) rank2 = (unsigned int)__popc(m2 & lt);
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive prefix over the 128 (class, key, warp) counts: 4 per lane + a warp scan
+        unsigned int c[4], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { c[j] = sh[lane * 4 + j]; sum += c[j]; }
+        unsigned int incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+        unsigned int run = incl - sum;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { sh[lane * 4 + j] = run; run += c[j]; }
+        if (lane == 31) sh[128] = incl ? atomicAdd(counter, incl) : 0u;
+    }
+    __syncthreads();
+    const unsigned int base = sh[128];
+    slot1 = base + sh[(key1 & 7) * 8 + warp] + rank1;
+    slot2 = base + sh[64 + (key2 & 7) * 8 + warp] + rank2;
+    __syncthreads();  // sh is reused by the next call
+}
+
+RT_DEV int direction_octant(float x, float y, float z) { return (x < 0.0f ? 1 : 0) | (y < 0.0f ? 2 : 0) | (z < 0.0f ? 4 : 0); }
 
 // ---------------------------------------------------------------------------------------------
 // gen_kernel: primary rays of units [unit0, unit0 + n_units); a unit = (8x4 pixel block, sample),
@@ -596,7 +635,7 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
     const unsigned int n = min(lv[L_RAYS], (unsigned int)p.capacity);
     const float4* __restrict__ q = p.q[level & 1];
     float4* __restrict__ qn = p.q[(level + 1) & 1];
-    __shared__ unsigned int sh_reserve[20];
+    __shared__ unsigned int sh_reserve[132];
     const unsigned int n_round = (n + 255u) & ~255u;  // whole 256-thread blocks take part in block_reserve2
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         const bool live = i < n;
@@ -728,7 +767,8 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
             }
         }
         unsigned int s_refl, s_refr;  // the block's reflection rays, then its refraction rays
-        block_reserve2(lv_next + L_RAYS, want_refl, want_refr, sh_reserve, s_refl, s_refr);
+        if (p.sort_emit) block_reserve_keyed(lv_next + L_RAYS, want_refl, direction_octant(rx, ry, rz), want_refr, direction_octant(tx, ty, tz), sh_reserve, s_refl, s_refr);
+        else block_reserve2(lv_next + L_RAYS, want_refl, want_refr, sh_reserve, s_refl, s_refr);
         if (want_refl) {
             if (s_refl < (unsigned int)p.capacity) {
                 float4* o = qn + (size_t)s_refl * 3;  // secondary rays carry the default time 0 (shapes.hpp:28)
@@ -1699,6 +1739,8 @@ static int render_impl(HostScene& h, const rt_render_params& rp, uint8_t* rgb8, 
     if ((rc = ensure_plan(d, k, rp.reserved[5], stream, &plan)) != RT_OK) return rc;
     if (plan_out) *plan_out = plan;
     k.packed = packed ? 1 : 0;
+    static const bool sort_emit = [] { const char* e = std::getenv("RT_B200_SORT_EMIT"); return e && e[0] == '1'; }();
+    k.sort_emit = sort_emit ? 1 : 0;
     if (!k.bvh.prune && k.bvh.use_bvh && !d->ref_tree && !h.tree.empty()) {
         static_assert(sizeof(TreeNode) == 40, "RefNode layout of traverse_reference_impl: 10 words per node");
         CUDA_TRY(cudaMalloc((void**)&d->ref_tree, h.tree.size() * sizeof(TreeNode)));
