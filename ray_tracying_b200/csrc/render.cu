@@ -460,16 +460,17 @@ RT_DEV void packet_loop(const BvhView& bvh, Src& src, unsigned int* counter, uns
                     const unsigned int bk = (k == 0 ? b0 : (k == 1 ? b1 : (k == 2 ? b2 : b3))) & alive;
                     if (bk == 0u) continue;
                     const int idx = __float_as_int(k == 0 ? C.v[3] : (k == 1 ? C.v[4] : (k == 2 ? C.v[5] : C.v[6])));
-                    const bool mine = ((bk >> lane) & 1u) && gate_passes(bvh, s, idx);
+                    const bool mine = (bk >> lane) & 1u;
                     const unsigned int type = (meta >> (16 + 2 * k)) & 3u;  // warp-uniform
                     Hit h;
                     bool hit = false;
                     if (type == RT_PLANE) { if (mine) hit = intersect_prim<false, PRIM_PLANE>(bvh.prims, idx, s.r, h); }
                     else { if (mine) hit = intersect_prim<false, PRIM_XFORM>(bvh.prims, idx, s.r, h); }
                     if (STATS && mine) st.prims++;
+                    // the gate only for a hit that would change the lane's answer
                     if (hit) {
-                        if (ANY) { if (!(h.t > s.max_t)) { s.best_prim = 0; active = false; } }
-                        else if (h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) {
+                        if (ANY) { if (!(h.t > s.max_t) && gate_passes(bvh, s, idx)) { s.best_prim = 0; active = false; } }
+                        else if ((h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) && gate_passes(bvh, s, idx)) {
                             s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
                         }
                     }

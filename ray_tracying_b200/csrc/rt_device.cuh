@@ -649,7 +649,8 @@ RT_DEV void trav_step(const BvhView& b, TravState& s, unsigned int stride, Trace
 }
 
 // The gate of primitive `idx` (sorted position): does the exact box of its reference leaf pass the
-// reference's AABB::intersect for this ray? Conservative test first; the reference's own arithmetic
+// reference's AABB::intersect for this ray? (Asked only for a primitive whose routine reported a hit that would
+// change the answer: "the reference tests the shape" AND "the shape is hit" commute.) Conservative test first; the reference's own arithmetic
 // (out of line, rare) when that is too close to call, and always for rays with a component |d_i| <= 1e-6
 // (KS = infinity, see the comment above TravState).
 RT_DEV bool gate_passes(const BvhView& b, const TravState& s, int idx) {
@@ -689,14 +690,13 @@ RT_DEV void trav_prims(const BvhView& b, TravState& s, TraceStats& st) {
                 m_x &= m_x - 1u;
                 const int idx = __float_as_int(__ldg(w + 27 + k));
                 Hit h;
-                if (gate_passes(b, s, idx)) {
-                    if (STATS) st.prims++;
-                    if (intersect_prim<false, PRIM_XFORM>(b.prims, idx, s.r, h)) {
-                        if (ANY) {
-                            if (!(h.t > s.max_t)) { occluded = true; m_x = 0u; m_p = 0u; }
-                        } else if (h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) {
-                            s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
-                        }
+                if (STATS) st.prims++;
+                // the routine first, the gate only for a hit that would change the answer (most candidates miss)
+                if (intersect_prim<false, PRIM_XFORM>(b.prims, idx, s.r, h)) {
+                    if (ANY) {
+                        if (!(h.t > s.max_t) && gate_passes(b, s, idx)) { occluded = true; m_x = 0u; m_p = 0u; }
+                    } else if ((h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) && gate_passes(b, s, idx)) {
+                        s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
                     }
                 }
             }
@@ -707,14 +707,13 @@ RT_DEV void trav_prims(const BvhView& b, TravState& s, TraceStats& st) {
                 m_p &= m_p - 1u;
                 const int idx = __float_as_int(__ldg(w + 27 + k));
                 Hit h;
-                if (gate_passes(b, s, idx)) {
-                    if (STATS) st.prims++;
-                    if (intersect_prim<false, PRIM_PLANE>(b.prims, idx, s.r, h)) {
-                        if (ANY) {
-                            if (!(h.t > s.max_t)) { occluded = true; m_p = 0u; }
-                        } else if (h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) {
-                            s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
-                        }
+                if (STATS) st.prims++;
+                // the routine first, the gate only for a hit that would change the answer (most candidates miss)
+                if (intersect_prim<false, PRIM_PLANE>(b.prims, idx, s.r, h)) {
+                    if (ANY) {
+                        if (!(h.t > s.max_t) && gate_passes(b, s, idx)) { occluded = true; m_p = 0u; }
+                    } else if ((h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) && gate_passes(b, s, idx)) {
+                        s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
                     }
                 }
             }
