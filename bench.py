@@ -113,12 +113,12 @@ def reference_sample(name: str, scene_path: str, render: dict, repeats: int, tar
             pass
 
     # rays per pixel from a probe with the port, then a window per process worth ~target_seconds of one core
-    # (0.13 Mrays/s per core is what the reference does on this class of host; the time is MEASURED below)
+    # (0.07-0.11 Mrays/s per core is what the reference does on the GPU boxes' hosts; the time is MEASURED below)
     probe_rows = (int(0.55 * height), int(0.55 * height) + 1)
     probe_cols = (int(0.4 * width), int(0.4 * width) + 64)
     probe = oracle.render(rows=probe_rows, cols=probe_cols, seed=1, **render)
     rays_per_px = max(1.0, sum(probe["rays"]) / 64.0)
-    target_px = max(8, int(0.13e6 * target_seconds * (1.0 if kind == "reference" else cores) / rays_per_px))
+    target_px = max(8, int(0.08e6 * target_seconds * (1.0 if kind == "reference" else cores) / rays_per_px))
     rows = max(1, min(height // procs, target_px // width))
     cols = width if target_px >= width else max(8, target_px)
     wins = []

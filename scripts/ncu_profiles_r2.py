@@ -26,7 +26,8 @@ KEYS = {
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio": "stall_wait",
     "sm__inst_executed.sum": "warp_instructions", "launch__grid_size": "grid",
 }
-UNIT = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0, "msecond": 1e3, "usecond": 1.0, "second": 1e6, "nsecond": 1e-3}
+UNIT = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0, "msecond": 1e3, "usecond": 1.0, "second": 1e6, "nsecond": 1e-3,
+        "ms": 1e3, "us": 1.0, "s": 1e6, "ns": 1e-3}
 
 
 def report(path):
