@@ -68,6 +68,9 @@ namespace rtb {
 #ifndef RT_WAVE_MINBLOCKS
 #define RT_WAVE_MINBLOCKS RT_TRACE_MINBLOCKS  /* resident blocks per SM of the per-ray kernels (trace_kernel, shadow_kernel) */
 #endif
+#ifndef RT_SHADE_MINBLOCKS
+#define RT_SHADE_MINBLOCKS 3  /* resident 256-thread blocks per SM of shade_kernel / light_kernel */
+#endif
 #ifndef RT_ANY_SORTED_PACKET
 #define RT_ANY_SORTED_PACKET 0
 #endif
@@ -631,7 +634,7 @@ RT_DEV void diffuse_color(const FrameParams& p, const float4 m0, int tex, float 
 // shadow and light kernels) and the reflection / refraction rays of the next level.
 // Trace() raytracer.cpp:280-351, createReflectionRay :101-115, createRefractionRay :118-150.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ FrameParams p, int level) {
+__global__ void __launch_bounds__(256, RT_SHADE_MINBLOCKS) shade_kernel(const __grid_constant__ FrameParams p, int level) {
     unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
     unsigned int* lv_next = p.lvl + (level + 1) * RT_LVL_STRIDE;
     const unsigned int n = min(lv[L_RAYS], (unsigned int)p.capacity);
@@ -918,7 +921,7 @@ __global__ void __launch_bounds__(128) shadow_literal_kernel(const __grid_consta
 // light_kernel: Blinn-Phong sum of one shade record with the visibilities from shadow_kernel.
 // shade() raytracer.cpp:191-273, then Trace()'s local_contribution * localColor.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) light_kernel(const __grid_constant__ FrameParams p, int level) {
+__global__ void __launch_bounds__(256, RT_SHADE_MINBLOCKS) light_kernel(const __grid_constant__ FrameParams p, int level) {
     const unsigned int n = p.lvl[level * RT_LVL_STRIDE + L_RECS];
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4* rc = p.recs[level & 1] + (size_t)i * 5;
