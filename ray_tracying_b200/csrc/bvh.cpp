@@ -19,6 +19,7 @@
 #include <chrono>
 #include <cstring>
 #include <future>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <stdexcept>
@@ -292,44 +293,96 @@ struct SahBuilder {
     int alloc() { return next.fetch_add(1, std::memory_order_relaxed); }
     void set(int id, const UpNode& n) { nodes[(size_t)id] = n; }
 
+    static constexpr int NB = 16;
+    struct Bins {
+        Box node, cb;            // box of the items, bounds of their centroids
+        Box bins[3][NB];
+        int cnt[3][NB];
+    };
+    static int bin_of(const Box& b, int a, float lo, float scale) {
+        return std::min(NB - 1, std::max(0, (int)((0.5f * (b.lo[a] + b.hi[a]) - lo) * scale)));
+    }
+    // Big ranges (the top of the tree) are scanned by all threads; the outcome does not depend on how the range is
+    // cut (min / max and counts), and the partition below keeps the items' relative order.
+    static constexpr int PAR_RANGE = 1 << 17;
+
     // builds the sub-tree over items[lo, hi) and returns its node id
     int build(int lo, int hi, int par_depth) {
         const int me = alloc();
         UpNode n;
-        box_reset(n.box);
-        for (int k = lo; k < hi; ++k) box_merge(n.box, cull[(size_t)items[k]]);
+        const bool wide_scan = hi - lo >= PAR_RANGE;
+        Bins acc0;
+        box_reset(acc0.node);
+        box_reset(acc0.cb);
+        {   // pass 1: node box and centroid bounds
+            std::mutex mu;
+            auto scan = [&](size_t a, size_t b) {
+                Box nb, cb;
+                box_reset(nb);
+                box_reset(cb);
+                for (size_t k = (size_t)lo + a; k < (size_t)lo + b; ++k) {
+                    const Box& bx = cull[(size_t)items[k]];
+                    box_merge(nb, bx);
+                    for (int ax = 0; ax < 3; ++ax) {
+                        const float c = 0.5f * (bx.lo[ax] + bx.hi[ax]);
+                        cb.lo[ax] = std::min(cb.lo[ax], c);
+                        cb.hi[ax] = std::max(cb.hi[ax], c);
+                    }
+                }
+                std::lock_guard<std::mutex> lock(mu);
+                box_merge(acc0.node, nb);
+                box_merge(acc0.cb, cb);
+            };
+            if (wide_scan) parallel_chunks((size_t)(hi - lo), 1 << 15, scan);
+            else scan(0, (size_t)(hi - lo));
+        }
+        n.box = acc0.node;
         if (hi - lo == 1) {
             n.prim = items[lo];
             set(me, n);
             return me;
         }
-        constexpr int NB = 16;
-        Box cb;
-        box_reset(cb);
-        for (int k = lo; k < hi; ++k) {
-            const Box& b = cull[(size_t)items[k]];
-            for (int a = 0; a < 3; ++a) {
-                const float c = 0.5f * (b.lo[a] + b.hi[a]);
-                cb.lo[a] = std::min(cb.lo[a], c);
-                cb.hi[a] = std::max(cb.hi[a], c);
-            }
+        const Box cb = acc0.cb;
+        float scale3[3];
+        bool axis_ok[3];
+        for (int a = 0; a < 3; ++a) {
+            const float ext = cb.hi[a] - cb.lo[a];
+            axis_ok[a] = ext > 0.0f && ext < 1e30f;
+            scale3[a] = axis_ok[a] ? (float)NB / ext : 0.0f;
+        }
+        // pass 2: the items into 16 bins per axis
+        std::unique_ptr<Bins> total(new Bins());
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < NB; ++b) { box_reset(total->bins[a][b]); total->cnt[a][b] = 0; }
+        {
+            std::mutex mu;
+            auto scan = [&](size_t a0, size_t b0) {
+                std::unique_ptr<Bins> loc(new Bins());
+                for (int a = 0; a < 3; ++a) for (int b = 0; b < NB; ++b) { box_reset(loc->bins[a][b]); loc->cnt[a][b] = 0; }
+                for (size_t k = (size_t)lo + a0; k < (size_t)lo + b0; ++k) {
+                    const Box& bx = cull[(size_t)items[k]];
+                    for (int a = 0; a < 3; ++a) {
+                        if (!axis_ok[a]) continue;
+                        const int bi = bin_of(bx, a, cb.lo[a], scale3[a]);
+                        box_merge(loc->bins[a][bi], bx);
+                        loc->cnt[a][bi]++;
+                    }
+                }
+                std::lock_guard<std::mutex> lock(mu);
+                for (int a = 0; a < 3; ++a) for (int b = 0; b < NB; ++b) {
+                    if (loc->cnt[a][b]) box_merge(total->bins[a][b], loc->bins[a][b]);
+                    total->cnt[a][b] += loc->cnt[a][b];
+                }
+            };
+            if (wide_scan) parallel_chunks((size_t)(hi - lo), 1 << 15, scan);
+            else scan(0, (size_t)(hi - lo));
         }
         const int min_side = std::max(1, (int)(min_frac * (hi - lo)));
         int best_axis = -1, best_bin = -1;
         double best_cost = 1e300;
         for (int a = 0; a < 3; ++a) {
-            const float ext = cb.hi[a] - cb.lo[a];
-            if (!(ext > 0.0f) || !(ext < 1e30f)) continue;
-            Box bins[NB];
-            int cnt[NB];
-            for (int b = 0; b < NB; ++b) { box_reset(bins[b]); cnt[b] = 0; }
-            const float scale = (float)NB / ext;
-            for (int k = lo; k < hi; ++k) {
-                const Box& b = cull[(size_t)items[k]];
-                const int bi = std::min(NB - 1, std::max(0, (int)((0.5f * (b.lo[a] + b.hi[a]) - cb.lo[a]) * scale)));
-                box_merge(bins[bi], b);
-                cnt[bi]++;
-            }
+            if (!axis_ok[a]) continue;
+            const Box* bins = total->bins[a];
+            const int* cnt = total->cnt[a];
             double right_area[NB];
             int right_cnt[NB];
             Box acc;
@@ -354,12 +407,38 @@ struct SahBuilder {
         int mid = -1;
         if (best_axis >= 0) {
             const int a = best_axis;
-            const float scale = (float)NB / (cb.hi[a] - cb.lo[a]);
-            auto it = std::partition(items.begin() + lo, items.begin() + hi, [&](int t) {
-                const Box& b = cull[(size_t)t];
-                return std::min(NB - 1, std::max(0, (int)((0.5f * (b.lo[a] + b.hi[a]) - cb.lo[a]) * scale))) <= best_bin;
-            });
-            mid = (int)(it - items.begin());
+            const float scale = scale3[a];
+            auto left = [&](int t) { return bin_of(cull[(size_t)t], a, cb.lo[a], scale) <= best_bin; };
+            if (wide_scan) {
+                // parallel stable partition through a scratch copy: per-chunk counts, prefix, scatter
+                const size_t cnt_all = (size_t)(hi - lo);
+                const size_t chunks = std::min<size_t>(64, std::max<size_t>(1, cnt_all >> 15));
+                std::vector<size_t> nl(chunks + 1, 0);
+                std::vector<int> tmp(items.begin() + lo, items.begin() + hi);
+                parallel_chunks(chunks, 1, [&](size_t c0, size_t c1) {
+                    for (size_t c = c0; c < c1; ++c) {
+                        size_t k = 0;
+                        for (size_t i = cnt_all * c / chunks; i < cnt_all * (c + 1) / chunks; ++i) k += left(tmp[i]) ? 1 : 0;
+                        nl[c + 1] = k;
+                    }
+                });
+                for (size_t c = 0; c < chunks; ++c) nl[c + 1] += nl[c];
+                const size_t n_left = nl[chunks];
+                parallel_chunks(chunks, 1, [&](size_t c0, size_t c1) {
+                    for (size_t c = c0; c < c1; ++c) {
+                        const size_t i0 = cnt_all * c / chunks, i1 = cnt_all * (c + 1) / chunks;
+                        size_t l = (size_t)lo + nl[c], r = (size_t)lo + n_left + (i0 - nl[c]);
+                        for (size_t i = i0; i < i1; ++i) {
+                            if (left(tmp[i])) items[l++] = tmp[i];
+                            else items[r++] = tmp[i];
+                        }
+                    }
+                });
+                mid = lo + (int)n_left;
+            } else {
+                auto it = std::partition(items.begin() + lo, items.begin() + hi, left);
+                mid = (int)(it - items.begin());
+            }
         }
         if (mid <= lo || mid >= hi) {
             // no admissible SAH split (all centroids equal, or the balance bound excludes every bin boundary):
@@ -385,20 +464,25 @@ struct SahBuilder {
     }
 };
 
-// Collapses the binary tree to <= 4 children per node and writes the wide nodes breadth-first.
+// Collapses the binary tree to <= 4 children per node and writes the wide nodes breadth-first: a serial pass
+// decides the structure (which sub-trees become the children of which node, node numbers), a parallel pass fills
+// the 128-byte records.
 void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root, const std::vector<Box>& cull, const std::vector<float>& cq) {
-    struct Item { int up, wide, level, sp; };
-    std::vector<Item> queue;
-    queue.reserve(up.size() / 2 + 2);
-    queue.push_back({root, 0, 1, 0});
-    s.dwide.assign(1, empty_wide());
+    struct Plan { int up, level, sp, first; int slots[4]; int8_t n, ni; };
+    std::vector<float> area(up.size());
+    parallel_chunks(up.size(), 1 << 16, [&](size_t a, size_t b) { for (size_t i = a; i < b; ++i) area[i] = (float)half_area(up[i].box); });
+    std::vector<Plan> plan;
+    plan.reserve(up.size() / 2 + 2);
+    plan.push_back({root, 1, 0, 0, {0, 0, 0, 0}, 0, 0});
     s.stack_need = 1;
     s.wide_depth = 0;
-    for (size_t qi = 0; qi < queue.size(); ++qi) {
-        const Item it = queue[qi];
+    size_t n_nodes = 1;
+    for (size_t qi = 0; qi < plan.size(); ++qi) {
+        Plan it = plan[qi];
         s.wide_depth = std::max(s.wide_depth, it.level);
         const UpNode& u = up[(size_t)it.up];
-        int slots[4], n = 0;
+        int* slots = it.slots;
+        int n = 0;
         if (u.left < 0) slots[n++] = it.up;  // a scene of one primitive: the root holds it
         else {
             slots[n++] = u.left;
@@ -406,9 +490,9 @@ void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root, const
         }
         while (n < 4) {  // open the inner child with the largest surface area
             int pick = -1;
-            double area = -1.0;
+            float best = -1.0f;
             for (int k = 0; k < n; ++k)
-                if (up[(size_t)slots[k]].left >= 0 && half_area(up[(size_t)slots[k]].box) > area) { area = half_area(up[(size_t)slots[k]].box); pick = k; }
+                if (up[(size_t)slots[k]].left >= 0 && area[(size_t)slots[k]] > best) { best = area[(size_t)slots[k]]; pick = k; }
             if (pick < 0) break;
             const int c = slots[pick];
             slots[pick] = up[(size_t)c].left;
@@ -418,39 +502,55 @@ void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root, const
         std::stable_partition(slots, slots + n, [&](int c) { return up[(size_t)c].left >= 0; });
         int ni = 0;
         while (ni < n && up[(size_t)slots[ni]].left >= 0) ++ni;
-        const int first = (int)s.dwide.size();
-        if (first + ni >= (1 << 30)) throw std::runtime_error("too many BVH nodes");
-        s.dwide.resize((size_t)first + ni, empty_wide());
-        DWide w = empty_wide();
-        uint32_t meta = 0;
-        float qmax = 0.0f;
-        for (int k = 0; k < n; ++k) {
-            const UpNode& c = up[(size_t)slots[k]];
-            meta |= 1u << k;
-            if (c.left < 0) {
-                // a primitive child carries its own (tight) culling box; Q of the node = the largest of its spheres
-                const HostPrim& p = s.prims[(size_t)s.order[(size_t)c.prim]];
-                set_child_box(w, k, cull[(size_t)c.prim]);
-                meta |= (16u << k) | ((uint32_t)p.type << (16 + 2 * k));
-                w.f[27 + k] = bits_f((uint32_t)c.prim);
-                qmax = std::max(qmax, cq[(size_t)c.prim]);
-            } else {
-                set_child_box(w, k, c.box);
-            }
-        }
-        w.f[24] = bits_f((uint32_t)first);
-        w.f[25] = bits_f(meta);
-        w.f[26] = qmax;
-        s.dwide[(size_t)it.wide] = w;
+        if (n_nodes + (size_t)ni >= (1u << 30)) throw std::runtime_error("too many BVH nodes");
+        it.first = (int)n_nodes;
+        it.n = (int8_t)n;
+        it.ni = (int8_t)ni;
+        plan[qi] = it;
         // the traversal pushes up to ni - 1 sibling nodes before it descends: the stack a ray can need below here
-        s.stack_need = std::max(s.stack_need, it.sp + std::max(0, ni - 1) + 1);
-        for (int k = 0; k < ni; ++k) queue.push_back({slots[k], first + k, it.level + 1, it.sp + std::max(0, ni - 1)});
+        const int pushed = std::max(0, ni - 1);
+        s.stack_need = std::max(s.stack_need, it.sp + pushed + 1);
+        for (int k = 0; k < ni; ++k) plan.push_back({slots[k], it.level + 1, it.sp + pushed, 0, {0, 0, 0, 0}, 0, 0});
+        n_nodes += (size_t)ni;
     }
+    s.dwide.assign(n_nodes, empty_wide());
+    parallel_chunks(plan.size(), 1 << 14, [&](size_t a, size_t b) {
+        for (size_t qi = a; qi < b; ++qi) {
+            const Plan& it = plan[qi];
+            DWide& w = s.dwide[qi];  // breadth-first: the qi-th planned node is node qi
+            uint32_t meta = 0;
+            float qmax = 0.0f;
+            for (int k = 0; k < it.n; ++k) {
+                const UpNode& c = up[(size_t)it.slots[k]];
+                meta |= 1u << k;
+                if (c.left < 0) {
+                    // a primitive child carries its own (tight) culling box; Q of the node = the largest of its spheres
+                    const HostPrim& p = s.prims[(size_t)s.order[(size_t)c.prim]];
+                    set_child_box(w, k, cull[(size_t)c.prim]);
+                    meta |= (16u << k) | ((uint32_t)p.type << (16 + 2 * k));
+                    w.f[27 + k] = bits_f((uint32_t)c.prim);
+                    qmax = std::max(qmax, cq[(size_t)c.prim]);
+                } else {
+                    set_child_box(w, k, c.box);
+                }
+            }
+            w.f[24] = bits_f((uint32_t)it.first);
+            w.f[25] = bits_f(meta);
+            w.f[26] = qmax;
+        }
+    });
 }
 
 }  // namespace
 
 void flatten_scene(HostScene& s) {
+    const bool timing = std::getenv("RT_B200_DEBUG") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        const auto now = std::chrono::steady_clock::now();
+        if (timing) std::fprintf(stderr, "[rt_b200] flatten: %s %.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
     const int n = (int)s.prims.size();
     // primitives in sorted order
     s.dprims.assign((size_t)n, DPrim{});
@@ -486,6 +586,7 @@ void flatten_scene(HostScene& s) {
         }
     }
     });
+    lap("primitive records + gate boxes");
     s.dwide.clear();
     s.wide_depth = 0;
     s.stack_need = 1;
@@ -536,6 +637,7 @@ void flatten_scene(HostScene& s) {
                 cq[k] = q;
             }
         });
+        lap("culling boxes");
         // the traversal stacks live in shared memory (36 entries x 6 blocks is what an SM holds): a tree that could
         // need more is rebuilt with a balance bound
         for (double min_frac : {0.0, 0.2, 0.35, 0.5}) {
@@ -544,7 +646,9 @@ void flatten_scene(HostScene& s) {
             for (int k = 0; k < n; ++k) b.items[(size_t)k] = k;
             b.nodes.resize(2 * (size_t)n);
             const int root = b.build(0, n, 6);
+            lap("SAH build");
             emit_wide_tree(s, b.nodes, root, cull, cq);
+            lap("collapse + emit");
             if (std::getenv("RT_B200_DEBUG")) std::fprintf(stderr, "[rt_b200] device tree: min_frac %.2f -> %zu nodes, depth %d, stack need %d\n", min_frac, s.dwide.size(), s.wide_depth, s.stack_need);
             if (s.stack_need <= 36) break;
         }

@@ -69,7 +69,7 @@ namespace rtb {
 #define RT_WAVE_MINBLOCKS RT_TRACE_MINBLOCKS  /* resident blocks per SM of the per-ray kernels (trace_kernel, shadow_kernel) */
 #endif
 #ifndef RT_SHADE_MINBLOCKS
-#define RT_SHADE_MINBLOCKS 3  /* resident 256-thread blocks per SM of shade_kernel / light_kernel */
+#define RT_SHADE_MINBLOCKS 4  /* resident 256-thread blocks per SM of shade_kernel / light_kernel (64 registers; 3 / 5 / 6 measured: shade -8 % at 4) */
 #endif
 #ifndef RT_ANY_SORTED_PACKET
 #define RT_ANY_SORTED_PACKET 0

@@ -26,31 +26,32 @@ def _pixel_function(width, height):
     return np.stack([(xs * 7 + ys * 3) % 251, (xs + ys * 5) % 241, (xs * ys) % 239], axis=-1).astype(np.uint8)
 
 
-def _worker(rank, world, port, width, height, tile, out_dir):
+def _worker(rank, world, port, width, height, tile, out_dir, block=0):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         truth = _pixel_function(width, height)
-        owner = rdist.tile_owner(width, height, tile, world)
+        owner = rdist.tile_owner(width, height, tile, world, block)
         local = np.zeros_like(truth)
         local[owner == rank] = truth[owner == rank]  # what rt_render_device leaves in a rank's frame
-        frame = rdist.gather_frame(torch.from_numpy(local), width, height, tile, rank, world)
+        frame = rdist.gather_frame(torch.from_numpy(local), width, height, tile, rank, world, block=block)
         np.save(os.path.join(out_dir, f"frame_{rank}.npy"), frame.numpy())
         # ids travel the same way (int32, one channel)
         ids_truth = (np.arange(width * height, dtype=np.int32).reshape(height, width) % 1000) - 1
         ids_local = np.full_like(ids_truth, -1)
         ids_local[owner == rank] = ids_truth[owner == rank]
-        ids = rdist.gather_frame(torch.from_numpy(ids_local)[..., None], width, height, tile, rank, world)[..., 0]
+        ids = rdist.gather_frame(torch.from_numpy(ids_local)[..., None], width, height, tile, rank, world, block=block)[..., 0]
         assert np.array_equal(ids.numpy(), ids_truth)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,width,height,tile", [(2, 100, 60, (32, 32)), (3, 97, 45, (16, 8)), (2, 64, 36, (8, 4))])
-def test_gather_frame_gloo(tmp_path, world, width, height, tile):
+@pytest.mark.parametrize("world,width,height,tile,block", [(2, 100, 60, (32, 32), 0), (3, 97, 45, (16, 8), 0), (2, 64, 36, (8, 4), 0),
+                                                         (2, 100, 60, (8, 4), 3)])
+def test_gather_frame_gloo(tmp_path, world, width, height, tile, block):
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, width, height, tile, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, width, height, tile, str(tmp_path), block), nprocs=world, join=True)
     truth = _pixel_function(width, height)
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"frame_{r}.npy"), truth)
@@ -65,3 +66,10 @@ def test_tile_owner_interleaves_tiles():
     assert counts.sum() == 6000 and rdist.max_rank_pixels(100, 60, (32, 32), 4) == counts.max()
     idx = rdist.rank_pixel_indices(100, 60, (32, 32), 4, 2)
     assert np.all(owner.reshape(-1)[idx] == 2) and len(idx) == counts[2]
+
+
+def test_tile_owner_in_blocks():
+    """block = B: B x B groups of tiles go to one rank (render.cu tile_owner): 8x4 tiles, blocks of 2 -> 16x8 pixel groups."""
+    owner = rdist.tile_owner(64, 32, (8, 4), 3, block=2)
+    assert (owner[:8, :16] == 0).all() and (owner[:8, 16:32] == 1).all() and (owner[:8, 32:48] == 2).all() and (owner[:8, 48:64] == 0).all()
+    assert (owner[8:16, :16] == 1).all()  # 4 blocks per row of blocks: the second row starts at block 4 -> rank 1
