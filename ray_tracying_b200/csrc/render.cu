@@ -580,7 +580,7 @@ struct ViewRays {
     int* hit_prim;
     // false: a dead slot (padding of a level-0 packet)
     RT_DEV bool load(long long item, Ray& r, float& max_t) const {
-        const float4 a = q[(size_t)item * 3 + 0], b = q[(size_t)item * 3 + 1];
+        const float4 a = ld_once_rw(q + (size_t)item * 3 + 0), b = ld_once_rw(q + (size_t)item * 3 + 1);
         r.ox = a.x; r.oy = a.y; r.oz = a.z; r.time = a.w;
         r.dx = b.x; r.dy = b.y; r.dz = b.z;
         max_t = 0.0f;
@@ -851,10 +851,10 @@ struct ShadowRaysT {
         }
         const unsigned int rec = (unsigned int)(rest / (unsigned int)cnt);
         const int k = (int)(rest % (unsigned int)cnt);
-        const float4 r0 = recs[(size_t)rec * 5 + 0];
+        const float4 r0 = ld_once_rw(recs + (size_t)rec * 5 + 0);
         if (__float_as_uint(r0.w) == RT_DEAD) return false;
         if (RT_SELF_OCCLUSION_SHADE && vis[(size_t)rec * p.n_lights + li] < 0) return false;  // settled in shade_kernel
-        const float4 r1 = recs[(size_t)rec * 5 + 1];
+        const float4 r1 = ld_once_rw(recs + (size_t)rec * 5 + 1);
         float tx = l0.x, ty = l0.y, tz = l0.z;
         const float radius = l1.w;
         if (radius > 0.0f) {

@@ -47,6 +47,31 @@ struct Hit {
 
 RT_DEV float dot3(float ax, float ay, float az, float bx, float by, float bz) { return ax * bx + ay * by + az * bz; }
 
+// Loads of data that is touched once per ray (primitive records, gate boxes, queue entries, shade records): they
+// go around L1 (RT_STREAM_LOADS = 1) so that L1 keeps what the traversal re-reads -- the BVH nodes.
+#ifndef RT_STREAM_LOADS
+#define RT_STREAM_LOADS 0
+#endif
+RT_DEV float4 ld_once(const float4* p) {
+#if RT_STREAM_LOADS
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+// ... the same for buffers another kernel wrote shortly before (no .nc)
+RT_DEV float4 ld_once_rw(const float4* p) {
+#if RT_STREAM_LOADS
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+
 // VecMath::normalize (raytracer.cpp:75-79) / Camera::normalize (camera.cpp:60-68)
 RT_DEV void normalize3(float& x, float& y, float& z) {
     const float mag = sqrtf(x * x + y * y + z * z);
@@ -143,15 +168,15 @@ enum PrimClass { PRIM_ANY = 0, PRIM_XFORM = 1, PRIM_PLANE = 2 };
 template <bool FULL, int CLS = PRIM_ANY>
 RT_DEV bool intersect_prim(const float4* __restrict__ prims, int idx, const Ray& r, Hit& h) {
     const float4* q = prims + (size_t)idx * 8;
-    const float4 q0 = __ldg(q + 0);
-    const float4 q1 = __ldg(q + 1);
-    const float4 q2 = __ldg(q + 2);
-    const float4 q3 = __ldg(q + 3);
+    const float4 q0 = ld_once(q + 0);
+    const float4 q1 = ld_once(q + 1);
+    const float4 q2 = ld_once(q + 2);
+    const float4 q3 = ld_once(q + 3);
     const int type = CLS == PRIM_PLANE ? (int)RT_PLANE : (int)(__float_as_uint(q0.w) & 3u);
 
     if (CLS != PRIM_XFORM && type == RT_PLANE) {
         // Plane::intersect (shapes.cpp:444-483); q1..q3 = corners 0..2 (+ corner 3 in .w), q4 = normal
-        const float4 q4 = __ldg(q + 4);
+        const float4 q4 = ld_once(q + 4);
         if (q4.w == 0.0f) return false;  // |cross| < 1e-6
         const float nx = q4.x, ny = q4.y, nz = q4.z;
         const float denom = dot3(nx, ny, nz, r.dx, r.dy, r.dz);
@@ -259,9 +284,9 @@ RT_DEV bool intersect_prim(const float4* __restrict__ prims, int idx, const Ray&
     }
 
     // back to world space (q4..q6 = object_to_world rows)
-    const float4 q4 = __ldg(q + 4);
-    const float4 q5 = __ldg(q + 5);
-    const float4 q6 = __ldg(q + 6);
+    const float4 q4 = ld_once(q + 4);
+    const float4 q5 = ld_once(q + 5);
+    const float4 q6 = ld_once(q + 6);
     float wx, wy, wz;
     xform_point(q4, q5, q6, plx, ply, plz, wx, wy, wz);
     if (type == RT_SPHERE) {
@@ -311,6 +336,12 @@ RT_DEV F8 ldg256(const float* p) {
 #ifdef RT_NO_LDG256
     const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
     r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+#endif
+#ifdef RT_NODE_EVICT_LAST
+    asm("ld.global.nc.L1::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+        : "l"(p));
     return r;
 #endif
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -654,7 +685,7 @@ RT_DEV void trav_step(const BvhView& b, TravState& s, unsigned int stride, Trace
 // (out of line, rare) when that is too close to call, and always for rays with a component |d_i| <= 1e-6
 // (KS = infinity, see the comment above TravState).
 RT_DEV bool gate_passes(const BvhView& b, const TravState& s, int idx) {
-    const float4 lo = __ldg(b.leafbox + 2 * (size_t)idx), hi = __ldg(b.leafbox + 2 * (size_t)idx + 1);
+    const float4 lo = ld_once(b.leafbox + 2 * (size_t)idx), hi = ld_once(b.leafbox + 2 * (size_t)idx + 1);
     if (!(s.KS > 3e38f)) {
         bool pass, sure;
         float ent;
