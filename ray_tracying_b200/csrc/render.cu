@@ -1649,9 +1649,9 @@ static int enqueue_frame(const HostScene& h, DeviceScene* d, FrameParams& k, boo
     d->class_of.clear();
     const long long n_batches = total_units > 0 ? (total_units + batch_units - 1) / batch_units : 0;
     // the cache only pays when a pixel's shadow rays come in several waves: more than one batch of samples
-    // (RT_B200_OCC_CACHE=2 forces it, 0 disables it); the counting pass runs without it (the work counters then say
-    // what the traversal costs when every ray is traversed)
-    const bool use_occ = k.occ_cache != nullptr && !collect && (n_batches > 1 || occ_mode == 2);
+    // (RT_B200_OCC_CACHE=2 forces it, 0 disables it); the counting pass and the per-kernel timing leg run without it
+    // (the work counters and the roofline then describe frames in which every shadow ray is traversed)
+    const bool use_occ = k.occ_cache != nullptr && !collect && !time_classes && (n_batches > 1 || occ_mode == 2);
     if (use_occ) CUDA_TRY(cudaMemsetAsync(k.occ_cache, 0xff, (size_t)n_pix * k.n_lights * sizeof(int), stream));
     const size_t max_pairs = time_classes ? (size_t)std::min<long long>(n_batches * (k.max_depth + 1) * 4, 1ll << 20) : 0;
     if (time_classes && d->class_ev.size() < 2 * max_pairs) {
