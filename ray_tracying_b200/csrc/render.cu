@@ -124,7 +124,6 @@ struct FrameParams {
     unsigned int* lvl;             // [RT_MAX_DEPTH + 2][RT_LVL_STRIDE] per-level counters
     unsigned long long* totals;    // [8] frame totals
     unsigned int* overflow_host;   // page-locked host word (mapped): set when a ray queue overflowed
-    int* occ_cache;                // last-occluder cache, one sorted position (or -1) per (pixel, light); may be null
     int capacity;                  // rays per queue
 };
 
@@ -474,7 +473,7 @@ RT_DEV void packet_loop(const BvhView& bvh, Src& src, unsigned int* counter, uns
                     else { if (mine) hit = intersect_prim<false, PRIM_XFORM>(bvh.prims, idx, s.r, h); }
                     if (STATS && mine) st.prims++;
                     if (hit) {
-                        if (ANY) { if (!(h.t > s.max_t)) { s.best_prim = idx; active = false; } }
+                        if (ANY) { if (!(h.t > s.max_t)) { s.best_prim = 0; active = false; } }
                         else if (h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) {
                             s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
                         }
@@ -829,14 +828,13 @@ __global__ void __launch_bounds__(RT_TRACE_THREADS, RT_TRACE_MINBLOCKS) trace_pa
 #ifndef RT_SELF_OCCLUSION
 #define RT_SELF_OCCLUSION 1
 #endif
-template <bool SELF, bool OCC>
+template <bool SELF>
 struct ShadowRaysT {
     const FrameParams& p;
     const float4* __restrict__ recs;  // this level's shade records
     int* vis;
     unsigned int n_recs;
-    unsigned int vis_idx;  // (record, light) of the ray in flight: index into vis
-    int occ_idx;           // its last-occluder cache entry (pixel, light), or -1
+    int* vis_slot;
     // false: the record is invalid (level 0: the view ray missed)
     RT_DEV bool load(long long item, Ray& sr, float& max_t) {
         unsigned long long rest = (unsigned long long)item;
@@ -880,50 +878,31 @@ struct ShadowRaysT {
                 if (!p.bvh.use_bvh || box_exact_call(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, sr)) return false;  // occluded by its own shape
             }
         }
-        vis_idx = rec * (unsigned int)p.n_lights + (unsigned int)li;
-        occ_idx = -1;
-        if (OCC && p.occ_cache != nullptr && p.bvh.prune && p.bvh.use_bvh) {
-            // Last-occluder cache: the shape that shadowed this pixel from this light a moment ago (an earlier
-            // batch of samples, another level) is tried first -- exact routine behind its gate (the reference tests a
-            // shape iff its leaf box passes). A hit closer than the light settles the query: the reference would
-            // find some occluder, and which one is irrelevant. A miss changes nothing.
-            occ_idx = (int)(__float_as_uint(r0.w) * (unsigned int)p.n_lights + (unsigned int)li);
-            const int c = p.occ_cache[occ_idx];
-            if (c >= 0) {
-                Hit h;
-                if (intersect_prim<false>(p.bvh.prims, c, sr, h) && !(h.t > max_t)) {
-                    const float4 blo = __ldg(p.bvh.leafbox + 2 * (size_t)c), bhi = __ldg(p.bvh.leafbox + 2 * (size_t)c + 1);
-                    if (box_exact_call(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, sr)) return false;
-                }
-            }
-        }
+        vis_slot = vis + (size_t)rec * p.n_lights + li;
         return true;
     }
-    // nothing closer than the light: this sample is lit (raytracer.cpp:233-235); otherwise remember the occluder
-    RT_DEV void store(long long, const TravState& s) const {
-        if (s.best_prim < 0) atomicAdd(vis + vis_idx, 1);
-        else if (OCC && occ_idx >= 0) p.occ_cache[occ_idx] = s.best_prim;
-    }
+    // nothing closer than the light: this sample is lit (raytracer.cpp:233-235)
+    RT_DEV void store(long long, const TravState& s) const { if (s.best_prim < 0) atomicAdd(vis_slot, 1); }
 };
-typedef ShadowRaysT<false, false> ShadowRays;  // literal mode: no shortcuts of any kind
+typedef ShadowRaysT<false> ShadowRays;
+typedef ShadowRaysT<RT_SELF_OCCLUSION != 0> ShadowRaysPacket;
 
-// OCC: with the last-occluder cache (frames whose pixels send their shadow rays in several waves).
-template <bool STATS, bool OCC>
+template <bool STATS>
 __global__ void __launch_bounds__(RT_TRACE_THREADS, RT_WAVE_MINBLOCKS) shadow_kernel(const __grid_constant__ FrameParams p, int level) {
     unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
     const unsigned long long n = (unsigned long long)lv[L_RECS] * (unsigned long long)p.shadow_per_rec;
     TraceStats st = {0u, 0u};
-    ShadowRaysT<false, OCC> src = {p, p.recs[level & 1], p.vis[level & 1], lv[L_RECS], 0u, -1};
+    ShadowRays src = {p, p.recs[level & 1], p.vis[level & 1], lv[L_RECS], nullptr};
     wave_loop<true, STATS>(p.bvh, src, lv + L_WORK_SHADOW, n, st);
     if (STATS) flush_stats(p, st);
 }
 
-template <bool STATS, bool OCC>
+template <bool STATS>
 __global__ void __launch_bounds__(RT_TRACE_THREADS, RT_TRACE_MINBLOCKS) shadow_packet_kernel(const __grid_constant__ FrameParams p, int level) {
     unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
     const unsigned long long n = (unsigned long long)lv[L_RECS] * (unsigned long long)p.shadow_per_rec;
     TraceStats st = {0u, 0u};
-    ShadowRaysT<RT_SELF_OCCLUSION != 0, OCC> src = {p, p.recs[level & 1], p.vis[level & 1], lv[L_RECS], 0u, -1};
+    ShadowRaysPacket src = {p, p.recs[level & 1], p.vis[level & 1], lv[L_RECS], nullptr};
     packet_loop<true, STATS>(p.bvh, src, lv + L_WORK_SHADOW, n, st);
     if (STATS) flush_stats(p, st);
 }
@@ -933,7 +912,7 @@ __global__ void __launch_bounds__(128) shadow_literal_kernel(const __grid_consta
     unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
     const unsigned long long n = (unsigned long long)lv[L_RECS] * (unsigned long long)p.shadow_per_rec;
     TraceStats st = {0u, 0u};
-    ShadowRays src = {p, p.recs[level & 1], p.vis[level & 1], lv[L_RECS], 0u, -1};
+    ShadowRays src = {p, p.recs[level & 1], p.vis[level & 1], lv[L_RECS], nullptr};
     literal_loop<true, STATS>(p.bvh, src, n, st);
     if (STATS) flush_stats(p, st);
 }
@@ -1202,8 +1181,6 @@ struct DeviceScene {
     int vis_lights = 0;
     unsigned long long* accum = nullptr;
     size_t accum_pixels = 0;
-    int* occ_cache = nullptr;   // last-occluder cache (pixels x lights), cleared at the start of every frame
-    size_t occ_entries = 0;
     unsigned int* lvl = nullptr;
     unsigned long long* totals = nullptr;
     unsigned int* overflow_host = nullptr;  // page-locked, mapped: set by shade_kernel when a queue overflows
@@ -1282,7 +1259,7 @@ static void free_device(DeviceScene* d) {
     if (d->own) cudaStreamDestroy(d->own);
     for (cudaEvent_t e : d->ev_shade) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : d->ev_light) if (e) cudaEventDestroy(e);
-    cudaFree(d->accum); cudaFree(d->occ_cache); cudaFree(d->lvl); cudaFree(d->totals);
+    cudaFree(d->accum); cudaFree(d->lvl); cudaFree(d->totals);
     if (d->overflow_host) cudaFreeHost(d->overflow_host);
     cudaFree(d->out_rgb); cudaFree(d->out_ids); cudaFree(d->out_lin);
     if (d->host_rgb) cudaFreeHost(d->host_rgb);
@@ -1389,15 +1366,14 @@ static int device_scene(HostScene& h, DeviceScene** out) {
         if (d->stack_bytes > 48 * 1024) {
             CUDA_TRY(cudaFuncSetAttribute(trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
             CUDA_TRY(cudaFuncSetAttribute(trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
-            CUDA_TRY(cudaFuncSetAttribute(shadow_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
-            CUDA_TRY(cudaFuncSetAttribute(shadow_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
-            CUDA_TRY(cudaFuncSetAttribute(shadow_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
+            CUDA_TRY(cudaFuncSetAttribute(shadow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
+            CUDA_TRY(cudaFuncSetAttribute(shadow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->stack_bytes));
         }
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_blocks, trace_kernel<false>, RT_TRACE_THREADS, d->stack_bytes));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->shadow_blocks, shadow_kernel<false, false>, RT_TRACE_THREADS, d->stack_bytes));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->shadow_blocks, shadow_kernel<false>, RT_TRACE_THREADS, d->stack_bytes));
         const size_t packet_smem0 = (size_t)(RT_TRACE_THREADS / 32) * d->packet_stack_depth * 16;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_packet_blocks, trace_packet_kernel<false>, RT_TRACE_THREADS, packet_smem0));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->shadow_packet_blocks, shadow_packet_kernel<false, false>, RT_TRACE_THREADS, packet_smem0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->shadow_packet_blocks, shadow_packet_kernel<false>, RT_TRACE_THREADS, packet_smem0));
         d->trace_blocks = std::max(1, d->trace_blocks);
         d->shadow_blocks = std::max(1, d->shadow_blocks);
         d->trace_packet_blocks = std::max(1, d->trace_packet_blocks);
@@ -1593,15 +1569,6 @@ static int ensure_buffers(DeviceScene* d, const FrameParams& k, long long batch_
         CUDA_TRY(cudaMalloc((void**)&d->accum, pixels * 3 * sizeof(unsigned long long)));
         d->accum_pixels = pixels;
     }
-    const size_t occ = pixels * (size_t)std::max(1, k.n_lights);
-    if (occ > d->occ_entries) {
-        CUDA_TRY(cudaDeviceSynchronize());
-        cudaFree(d->occ_cache);
-        d->occ_cache = nullptr;
-        d->occ_entries = 0;
-        CUDA_TRY(cudaMalloc((void**)&d->occ_cache, occ * sizeof(int)));
-        d->occ_entries = occ;
-    }
     return RT_OK;
 }
 
@@ -1621,11 +1588,6 @@ static int enqueue_frame(const HostScene& h, DeviceScene* d, FrameParams& k, boo
     for (int i = 0; i < 2; ++i) { k.recs[i] = d->recs[i]; k.vis[i] = d->vis[i]; }
     k.accum = d->accum; k.lvl = d->lvl; k.totals = d->totals;
     k.overflow_host = d->overflow_host;
-    const long long n_pix_all = (long long)k.res_x * k.res_y;
-    // the last-occluder cache pays when a pixel's shadow rays come in several waves (many batches of samples, deep
-    // recursion); it is cleared per frame, so a frame never depends on the one before
-    static const int occ_mode = [] { const char* e = std::getenv("RT_B200_OCC_CACHE"); return e ? std::atoi(e) : 1; }();
-    k.occ_cache = (occ_mode != 0 && k.n_lights > 0 && (long long)n_pix_all * k.n_lights < (1ll << 31)) ? d->occ_cache : nullptr;
     const int grid_trace = d->sm_count * d->trace_blocks, grid_trace_packet = d->sm_count * d->trace_packet_blocks;
     const int grid_shadow = d->sm_count * d->shadow_blocks, grid_shadow_packet = d->sm_count * d->shadow_packet_blocks;
     const int grid_wide = d->sm_count * 8;
@@ -1635,9 +1597,7 @@ static int enqueue_frame(const HostScene& h, DeviceScene* d, FrameParams& k, boo
     // allocation never shrinks, so halving the batch really halves the pressure on the queues).
     const long long overshoot = (long long)std::max(std::max(grid_trace, grid_shadow), std::max(grid_trace_packet, grid_shadow_packet)) * (RT_TRACE_THREADS / 32) * 128 + 65536;
     const long long work_cap = ((1ll << 32) - overshoot) / spr;
-    // (record, light) pairs are addressed with 32 bits
-    const long long vis_cap = ((1ll << 32) - 1) / std::max(1, k.n_lights);
-    k.capacity = (int)std::min<long long>(std::min<long long>(std::min<long long>(d->capacity, (1ll << 30)), work_cap), vis_cap);
+    k.capacity = (int)std::min<long long>(std::min<long long>(d->capacity, (1ll << 30)), work_cap);
 
     int launches = 0;
     CUDA_TRY(cudaMemsetAsync(d->lvl, 0, (RT_MAX_DEPTH + 2) * RT_LVL_STRIDE * sizeof(unsigned int), stream));
@@ -1645,14 +1605,8 @@ static int enqueue_frame(const HostScene& h, DeviceScene* d, FrameParams& k, boo
     const int n_pix = k.res_x * k.res_y;
     clear_accum_kernel<<<(n_pix + 255) / 256, 256, 0, stream>>>(k);
     ++launches;
-
     d->class_of.clear();
     const long long n_batches = total_units > 0 ? (total_units + batch_units - 1) / batch_units : 0;
-    // the cache only pays when a pixel's shadow rays come in several waves: more than one batch of samples
-    // (RT_B200_OCC_CACHE=2 forces it, 0 disables it); the counting pass and the per-kernel timing leg run without it
-    // (the work counters and the roofline then describe frames in which every shadow ray is traversed)
-    const bool use_occ = k.occ_cache != nullptr && !collect && !time_classes && (n_batches > 1 || occ_mode == 2);
-    if (use_occ) CUDA_TRY(cudaMemsetAsync(k.occ_cache, 0xff, (size_t)n_pix * k.n_lights * sizeof(int), stream));
     const size_t max_pairs = time_classes ? (size_t)std::min<long long>(n_batches * (k.max_depth + 1) * 4, 1ll << 20) : 0;
     if (time_classes && d->class_ev.size() < 2 * max_pairs) {
         const size_t have = d->class_ev.size();
@@ -1732,13 +1686,11 @@ static int enqueue_frame(const HostScene& h, DeviceScene* d, FrameParams& k, boo
                     if (collect) shadow_literal_kernel<true><<<grid_wide, 128, 0, aux>>>(k, level);
                     else shadow_literal_kernel<false><<<grid_wide, 128, 0, aux>>>(k, level);
                 } else if (shadow_packets) {
-                    if (collect) shadow_packet_kernel<true, false><<<grid_shadow_packet, RT_TRACE_THREADS, packet_smem, aux>>>(k, level);
-                    else if (use_occ) shadow_packet_kernel<false, true><<<grid_shadow_packet, RT_TRACE_THREADS, packet_smem, aux>>>(k, level);
-                    else shadow_packet_kernel<false, false><<<grid_shadow_packet, RT_TRACE_THREADS, packet_smem, aux>>>(k, level);
+                    if (collect) shadow_packet_kernel<true><<<grid_shadow_packet, RT_TRACE_THREADS, packet_smem, aux>>>(k, level);
+                    else shadow_packet_kernel<false><<<grid_shadow_packet, RT_TRACE_THREADS, packet_smem, aux>>>(k, level);
                 } else {
-                    if (collect) shadow_kernel<true, false><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, aux>>>(k, level);
-                    else if (use_occ) shadow_kernel<false, true><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, aux>>>(k, level);
-                    else shadow_kernel<false, false><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, aux>>>(k, level);
+                    if (collect) shadow_kernel<true><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, aux>>>(k, level);
+                    else shadow_kernel<false><<<grid_shadow, RT_TRACE_THREADS, d->stack_bytes, aux>>>(k, level);
                 }
                 mark_end(pr, aux);
                 ++launches;

@@ -702,7 +702,6 @@ RT_DEV bool gate_passes(const BvhView& b, const TravState& s, int idx) {
 template <bool ANY, bool STATS>
 RT_DEV void trav_prims(const BvhView& b, TravState& s, TraceStats& st) {
     bool occluded = false;
-    int occluder = 0;
 #pragma unroll 1
     for (int slot = 0; slot < RT_PEND_SLOTS; ++slot) {
         unsigned int m_x = 0u, m_p = 0u;
@@ -726,7 +725,7 @@ RT_DEV void trav_prims(const BvhView& b, TravState& s, TraceStats& st) {
                 // the routine first, the gate only for a hit that would change the answer (most candidates miss)
                 if (intersect_prim<false, PRIM_XFORM>(b.prims, idx, s.r, h)) {
                     if (ANY) {
-                        if (!(h.t > s.max_t) && gate_passes(b, s, idx)) { occluded = true; occluder = idx; m_x = 0u; m_p = 0u; }
+                        if (!(h.t > s.max_t) && gate_passes(b, s, idx)) { occluded = true; m_x = 0u; m_p = 0u; }
                     } else if ((h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) && gate_passes(b, s, idx)) {
                         s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
                     }
@@ -743,7 +742,7 @@ RT_DEV void trav_prims(const BvhView& b, TravState& s, TraceStats& st) {
                 // the routine first, the gate only for a hit that would change the answer (most candidates miss)
                 if (intersect_prim<false, PRIM_PLANE>(b.prims, idx, s.r, h)) {
                     if (ANY) {
-                        if (!(h.t > s.max_t) && gate_passes(b, s, idx)) { occluded = true; occluder = idx; m_p = 0u; }
+                        if (!(h.t > s.max_t) && gate_passes(b, s, idx)) { occluded = true; m_p = 0u; }
                     } else if ((h.t < s.best_t || (h.t == s.best_t && idx < s.best_prim)) && gate_passes(b, s, idx)) {
                         s.best_t = h.t; s.best_prim = idx; s.lim = prune_limit(s.best_t);
                     }
@@ -752,7 +751,7 @@ RT_DEV void trav_prims(const BvhView& b, TravState& s, TraceStats& st) {
         }
     }
     s.pend = 0u;
-    if (ANY && occluded) { s.best_prim = occluder; s.cur = RT_CUR_NONE; s.sp = s.sp0; }
+    if (ANY && occluded) { s.best_prim = 0; s.cur = RT_CUR_NONE; s.sp = s.sp0; }
 }
 
 // Warp-level work distribution for persistent kernels: the warp owns a pool [pool_lo, pool_hi)
