@@ -391,6 +391,13 @@ def run_ours(args, wl):
             with open(tp) as f:
                 captured = json.load(f)
 
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            with open(peaks_path) as f:
+                hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        else:
+            hbm_peak, hbm_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+
         def roofline(m):
             # Dominant kernels = the traversal loops (trace_kernel / shadow_kernel / their packet flavours): one
             # number for all of them, box tests per second, against the measured ceiling of the loop's node step.
@@ -398,9 +405,14 @@ def run_ours(args, wl):
             achieved = leg["my_box_tests"] / (leg["trav_ms"] * 1e-3) / 1e9
             peak = max(leg["peak_closest"], leg["peak_any"]) / 1e9
             cap = captured.get(m["name"]) if captured.get("kernel_source_tag") == tag else None
+            hbm = None
+            if cap:  # what the dominant kernel asks of HBM, against the driver-measured copy peak: a few % -- not the bound
+                dram_gbs = cap["dram_bytes_per_launch"] / (cap["duration_us"] * 1e-6) / 1e9
+                hbm = {"kernel": cap["kernel"], "dram_gbs": dram_gbs, "peak_gbs": hbm_peak, "frac": dram_gbs / hbm_peak, "peak_source": hbm_src}
             return {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "Gbox-tests/s", "frac": achieved / peak,
                     "traffic": cap["dram_bytes_per_launch"] if cap else None,
                     "traffic_source": (captured.get("source") if cap else "no ncu capture of these kernel sources under profiles/"),
+                    "hbm": hbm,
                     "peak_source": "rt_traversal_peak measured in this run: the loop's node step (4 slab tests, sorting network, 3 pushes, "
                                    "descent = full work) with converged warps on 64 L1-resident synthetic nodes; closest-hit %.1f / any-hit "
                                    "%.1f Gbox-tests/s" % (leg["peak_closest"] / 1e9, leg["peak_any"] / 1e9),

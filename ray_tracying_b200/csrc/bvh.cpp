@@ -284,9 +284,9 @@ inline void box_merge(Box& b, const Box& o) {
 }
 
 struct SahBuilder {
-    const std::vector<Box>& cull;   // ancestor box per sorted position (what the inner nodes must contain)
+    struct Item { Box box; int prim; };  // a primitive's ancestor box travels with it: every pass streams through memory
     double min_frac;                // a split must leave at least this share of the primitives on each side
-    std::vector<int> items;         // sorted positions, permuted in place
+    std::vector<Item> items;        // (ancestor box, sorted position), permuted in place
     std::vector<UpNode> nodes;      // pre-sized to 2n - 1: sub-trees built on other threads claim slots with `next`
     std::atomic<int> next{0};
 
@@ -321,7 +321,7 @@ struct SahBuilder {
                 box_reset(nb);
                 box_reset(cb);
                 for (size_t k = (size_t)lo + a; k < (size_t)lo + b; ++k) {
-                    const Box& bx = cull[(size_t)items[k]];
+                    const Box& bx = items[k].box;
                     box_merge(nb, bx);
                     for (int ax = 0; ax < 3; ++ax) {
                         const float c = 0.5f * (bx.lo[ax] + bx.hi[ax]);
@@ -338,7 +338,7 @@ struct SahBuilder {
         }
         n.box = acc0.node;
         if (hi - lo == 1) {
-            n.prim = items[lo];
+            n.prim = items[lo].prim;
             set(me, n);
             return me;
         }
@@ -359,7 +359,7 @@ struct SahBuilder {
                 std::unique_ptr<Bins> loc(new Bins());
                 for (int a = 0; a < 3; ++a) for (int b = 0; b < NB; ++b) { box_reset(loc->bins[a][b]); loc->cnt[a][b] = 0; }
                 for (size_t k = (size_t)lo + a0; k < (size_t)lo + b0; ++k) {
-                    const Box& bx = cull[(size_t)items[k]];
+                    const Box& bx = items[k].box;
                     for (int a = 0; a < 3; ++a) {
                         if (!axis_ok[a]) continue;
                         const int bi = bin_of(bx, a, cb.lo[a], scale3[a]);
@@ -408,13 +408,13 @@ struct SahBuilder {
         if (best_axis >= 0) {
             const int a = best_axis;
             const float scale = scale3[a];
-            auto left = [&](int t) { return bin_of(cull[(size_t)t], a, cb.lo[a], scale) <= best_bin; };
+            auto left = [&](const Item& t) { return bin_of(t.box, a, cb.lo[a], scale) <= best_bin; };
             if (wide_scan) {
                 // parallel stable partition through a scratch copy: per-chunk counts, prefix, scatter
                 const size_t cnt_all = (size_t)(hi - lo);
                 const size_t chunks = std::min<size_t>(64, std::max<size_t>(1, cnt_all >> 15));
                 std::vector<size_t> nl(chunks + 1, 0);
-                std::vector<int> tmp(items.begin() + lo, items.begin() + hi);
+                std::vector<Item> tmp(items.begin() + lo, items.begin() + hi);
                 parallel_chunks(chunks, 1, [&](size_t c0, size_t c1) {
                     for (size_t c = c0; c < c1; ++c) {
                         size_t k = 0;
@@ -446,9 +446,9 @@ struct SahBuilder {
             int a = 0;
             for (int i = 1; i < 3; ++i) if (cb.hi[i] - cb.lo[i] > cb.hi[a] - cb.lo[a]) a = i;
             mid = (lo + hi) / 2;
-            std::nth_element(items.begin() + lo, items.begin() + mid, items.begin() + hi, [&](int x, int y) {
-                const float cx = cull[(size_t)x].lo[a] + cull[(size_t)x].hi[a], cy = cull[(size_t)y].lo[a] + cull[(size_t)y].hi[a];
-                return cx < cy || (cx == cy && x < y);
+            std::nth_element(items.begin() + lo, items.begin() + mid, items.begin() + hi, [&](const Item& x, const Item& y) {
+                const float cx = x.box.lo[a] + x.box.hi[a], cy = y.box.lo[a] + y.box.hi[a];
+                return cx < cy || (cx == cy && x.prim < y.prim);
             });
         }
         if (par_depth > 0 && hi - lo > (1 << 14)) {
@@ -641,9 +641,9 @@ void flatten_scene(HostScene& s) {
         // the traversal stacks live in shared memory (36 entries x 6 blocks is what an SM holds): a tree that could
         // need more is rebuilt with a balance bound
         for (double min_frac : {0.0, 0.2, 0.35, 0.5}) {
-            SahBuilder b{abox, min_frac, {}, {}};
+            SahBuilder b{min_frac, {}, {}};
             b.items.resize((size_t)n);
-            for (int k = 0; k < n; ++k) b.items[(size_t)k] = k;
+            for (int k = 0; k < n; ++k) b.items[(size_t)k] = {abox[(size_t)k], k};
             b.nodes.resize(2 * (size_t)n);
             const int root = b.build(0, n, 6);
             lap("SAH build");

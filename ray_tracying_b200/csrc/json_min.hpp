@@ -118,6 +118,11 @@ public:
     // every other member).
     void defer(std::vector<std::string> keys, std::vector<DeferredArray>* out) { defer_keys_ = std::move(keys); deferred_ = out; }
 
+    // The value of this key of the ROOT object is not parsed either: it becomes Null and its text range is
+    // reported (the loader memoises material blocks by their text: a scene repeats a handful of them millions
+    // of times).
+    void skip_key(const char* key, std::pair<const char*, const char*>* range) { skip_key_ = key; skip_range_ = range; }
+
     Value parse_document() {
         depth_ = 0;
         Value v = parse_value();
@@ -129,6 +134,8 @@ public:
 private:
     std::vector<std::string> defer_keys_;
     std::vector<DeferredArray>* deferred_ = nullptr;
+    const char* skip_key_ = nullptr;
+    std::pair<const char*, const char*>* skip_range_ = nullptr;
     int depth_ = 0;
 
     // Skips one value without building it; the text must be well formed as far as brackets and strings go
@@ -375,7 +382,13 @@ private:
                 if (p_ != end_ && *p_ == '[')
                     for (const std::string& k : defer_keys_) if (k == key) deferred = true;
             }
-            if (deferred) {
+            if (root && skip_key_ && key == skip_key_) {
+                skip_ws();
+                const char* b = p_;
+                skip_value();
+                *skip_range_ = std::make_pair(b, p_);  // the last duplicate wins, like every other member
+                child.kind = Value::Null;
+            } else if (deferred) {
                 defer_array(key);
                 child.kind = Value::Array;
                 child.box.reset(new Value::Box());
@@ -408,6 +421,13 @@ inline Value parse(const std::string& text) {
 // One element of a deferred array.
 inline Value parse_range(const char* begin, const char* end) {
     Parser p(begin, end);
+    return p.parse_document();
+}
+// ... with the value of root key `key` left unparsed (Null) and its text range in `range` ({nullptr, nullptr} if absent).
+inline Value parse_range_skipping(const char* begin, const char* end, const char* key, std::pair<const char*, const char*>& range) {
+    range = std::make_pair((const char*)nullptr, (const char*)nullptr);
+    Parser p(begin, end);
+    p.skip_key(key, &range);
     return p.parse_document();
 }
 

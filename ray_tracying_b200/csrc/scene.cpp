@@ -295,14 +295,21 @@ struct ShapeOut {
     explicit ShapeOut(HostPrim& slot) : prim(slot) {}
 };
 
-void convert_shape(int type, const Value& j, ShapeOut& o) {
+// A parsed "material" block: what parse_material returned for its text.
+struct MaterialEntry {
+    rt_material_desc mat;
+    std::string texture_file, warn;
+};
+
+// `material` = the element's parsed material block, or nullptr when the element has none (default material).
+void convert_shape(int type, const Value& j, const MaterialEntry* material, ShapeOut& o) {
     static const float zero3[3] = {0, 0, 0};
     o.ok = false;
     if (!j.is_object()) return;
-    auto material_of = [&](const Value& e) {
+    auto material_of = [&](const Value&) {
         o.mat = default_material();
         o.texture_file.clear();
-        if (const Value* mj = e.find("material")) o.mat = parse_material(*mj, o.texture_file, o.warn);
+        if (material) { o.mat = material->mat; o.texture_file = material->texture_file; o.warn += material->warn; }
     };
     try {
         if (type == RT_SPHERE) {  // json_loader.cpp:180-234
@@ -392,16 +399,32 @@ void load_shapes(const std::vector<jsonmin::DeferredArray>& arrays, HostScene& s
         std::vector<std::string> fatal(threads);
         auto work = [&](unsigned t) {
             const size_t lo = n * t / threads, hi = n * (t + 1) / threads;
+            // material blocks memoised by their text (per thread): a scene repeats a handful of them millions of times
+            std::unordered_map<std::string, MaterialEntry> seen;
             for (size_t i = lo; i < hi; ++i) {
                 Value j;
+                const MaterialEntry* material = nullptr;
                 try {
-                    j = jsonmin::parse_range(arr->elements[i].first, arr->elements[i].second);
+                    std::pair<const char*, const char*> mr;
+                    j = jsonmin::parse_range_skipping(arr->elements[i].first, arr->elements[i].second, "material", mr);
+                    if (mr.first) {
+                        std::string text(mr.first, mr.second);
+                        auto it = seen.find(text);
+                        if (it == seen.end()) {
+                            MaterialEntry e;
+                            const Value mj = jsonmin::parse_range(mr.first, mr.second);
+                            e.mat = parse_material(mj, e.texture_file, e.warn);
+                            if (seen.size() > 4096) seen.clear();  // scenes with a material per shape: no point in remembering them
+                            it = seen.emplace(std::move(text), std::move(e)).first;
+                        }
+                        material = &it->second;
+                    }
                 } catch (const std::exception& e) {  // malformed JSON: the whole document is rejected, like the reference's parse
                     if (fatal[t].empty()) fatal[t] = e.what();
                     return;
                 }
                 ShapeOut o(s.prims[base + i]);
-                convert_shape(types[c], j, o);
+                convert_shape(types[c], j, material, o);
                 ok[i] = o.ok ? 1 : 0;
                 mat[i] = o.mat;
                 if (!o.texture_file.empty() || !o.warn.empty()) notes[t].push_back({i, std::move(o.texture_file), std::move(o.warn)});

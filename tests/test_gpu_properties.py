@@ -48,3 +48,19 @@ def test_culling_boxes_contain_every_exact_hit_large_scene(rt, tmp_path):
     r = scene.selftest_cull(rays_per_primitive=2000, seed=3)
     assert r["violations"] == 0, r
     assert r["hits"] > 1_000_000
+
+
+def test_traversal_ceiling_and_launch_accounting(rt):
+    """rt_traversal_peak (the roofline denominator of bench.py) returns a plausible, repeatable rate for both query
+    flavours, and rt_scene_launch_count adds exactly what each frame reports."""
+    import os
+    from conftest import GOLDEN
+    scene = rt.Scene.from_json(os.path.join(GOLDEN, "mixed_400.json"), GOLDEN)
+    a, ms_a = scene.traversal_peak(any_hit=False, steps=2048, repeats=3)
+    b, _ = scene.traversal_peak(any_hit=True, steps=2048, repeats=3)
+    a2, _ = scene.traversal_peak(any_hit=False, steps=2048, repeats=3)
+    assert 2e10 < a < 5e12 and 2e10 < b < 5e12 and ms_a > 0
+    assert abs(a - a2) / a < 0.1
+    n0 = scene.launch_count()
+    st = scene.render(use_bvh=True, n_samples_sqrt=1, fixed_time=0.0, max_depth=3)[3]
+    assert scene.launch_count() - n0 == st.launches == 1 + 1 + 4 * 4 + 1 + 1
