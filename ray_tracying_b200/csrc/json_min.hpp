@@ -15,6 +15,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -123,6 +124,9 @@ public:
     // of times).
     void skip_key(const char* key, std::pair<const char*, const char*>* range) { skip_key_ = key; skip_range_ = range; }
 
+    // Deferred arrays of more than a few MB are scanned by this many threads (1 = always the serial scan).
+    void set_threads(unsigned n) { threads_ = n ? n : 1; }
+
     Value parse_document() {
         depth_ = 0;
         Value v = parse_value();
@@ -137,6 +141,143 @@ private:
     const char* skip_key_ = nullptr;
     std::pair<const char*, const char*>* skip_range_ = nullptr;
     int depth_ = 0;
+    unsigned threads_ = 1;
+
+    static bool is_ws(char c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r'; }
+
+    // first byte in [q, e) that is one of " { } [ ] (and , if `comma`), or e
+    static const char* next_structural(const char* q, const char* e, bool comma) {
+#if defined(__SSE2__)
+        while (e - q >= 16) {
+            const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(q));
+            const __m128i f = _mm_or_si128(v, _mm_set1_epi8(0x20));
+            __m128i hit = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(f, _mm_set1_epi8('{')), _mm_cmpeq_epi8(f, _mm_set1_epi8('}'))),
+                                       _mm_cmpeq_epi8(v, _mm_set1_epi8('"')));
+            if (comma) hit = _mm_or_si128(hit, _mm_cmpeq_epi8(v, _mm_set1_epi8(',')));
+            const int mask = _mm_movemask_epi8(hit);
+            if (mask) return q + __builtin_ctz((unsigned)mask);
+            q += 16;
+        }
+#endif
+        for (; q < e; ++q) {
+            const char c = *q;
+            if (c == '"' || c == '{' || c == '}' || c == '[' || c == ']' || (comma && c == ',')) return q;
+        }
+        return e;
+    }
+
+    // A '"' is a string delimiter unless an odd number of backslashes stands before it (only meaningful inside
+    // strings; outside, a backslash is malformed and the element's own parse will say so).
+    static bool real_quote(const char* q, const char* region_begin) {
+        int n = 0;
+        while (q - n - 1 >= region_begin && *(q - n - 1) == '\\') ++n;
+        return (n & 1) == 0;
+    }
+
+    // The REST of an array -- p_ stands at the first byte of an element, bracket depth 1 -- scanned by several threads:
+    //   pass A: string delimiters per chunk            -> is each chunk's first byte inside a string?
+    //   pass B: bracket depth change per chunk          -> depth at each chunk's first byte, chunk in which the array closes
+    //   pass C: commas at depth 1 and the closing ']'   -> element boundaries
+    // Appends the elements to d and leaves p_ behind the ']'. Returns false (nothing consumed, nothing appended) whenever
+    // the outcome is not a plain list of non-empty elements: the serial scan then continues and reports malformed input
+    // exactly as before.
+    bool defer_rest_parallel(DeferredArray* d) {
+        const char* const rb = p_;
+        const size_t len = (size_t)(end_ - rb);
+        const size_t chunks = std::min<size_t>((size_t)threads_ * 4, len >> 20);
+        if (threads_ < 2 || chunks < 2) return false;
+        auto cb = [&](size_t c) { return rb + len * c / chunks; };
+        auto run = [&](auto fn) {
+            std::vector<std::thread> pool;
+            const unsigned t_n = (unsigned)std::min<size_t>(threads_, chunks);
+            for (unsigned t = 1; t < t_n; ++t) pool.emplace_back([=] { for (size_t c = t; c < chunks; c += t_n) fn(c); });
+            for (size_t c = 0; c < chunks; c += t_n) fn(c);
+            for (std::thread& th : pool) th.join();
+        };
+        std::vector<size_t> quotes(chunks, 0);
+        run([&](size_t c) {
+            size_t n = 0;
+            const char* e = cb(c + 1);
+            for (const char* q = cb(c); q < e; ++q) {
+                q = static_cast<const char*>(std::memchr(q, '"', (size_t)(e - q)));
+                if (!q) break;
+                if (real_quote(q, rb)) ++n;
+            }
+            quotes[c] = n;
+        });
+        std::vector<char> in_str(chunks + 1, 0);
+        for (size_t c = 0; c < chunks; ++c) in_str[c + 1] = (char)((in_str[c] + quotes[c]) & 1);
+        // per chunk: net change of the bracket depth, and the lowest depth reached right after a closing bracket
+        // (relative to the chunk's first byte; "none" if the chunk closes nothing)
+        const long long NONE = (long long)1 << 60;
+        std::vector<long long> delta(chunks, 0), low(chunks, NONE);
+        run([&](size_t c) {
+            bool s = in_str[c] != 0;
+            long long dep = 0, mn = NONE;
+            const char* e = cb(c + 1);
+            for (const char* q = next_structural(cb(c), e, false); q < e; q = next_structural(q + 1, e, false)) {
+                const char ch = *q;
+                if (ch == '"') { if (real_quote(q, rb)) s = !s; }
+                else if (!s) {
+                    if (ch == '{' || ch == '[') ++dep;
+                    else { --dep; mn = std::min(mn, dep); }
+                }
+            }
+            delta[c] = dep;
+            low[c] = mn;
+        });
+        // the region starts at depth 1: the array closes in the first chunk in which a closing bracket brings the depth
+        // to 0 (pass C finds the byte)
+        std::vector<long long> dep0(chunks + 1, 1);
+        size_t last = chunks;
+        for (size_t c = 0; c < chunks; ++c) {
+            if (last == chunks && low[c] != NONE && dep0[c] + low[c] <= 0) last = c;
+            dep0[c + 1] = dep0[c] + delta[c];
+        }
+        if (last == chunks) return false;  // unterminated: let the serial scan report it
+        std::vector<std::vector<const char*>> commas(last + 1);
+        std::vector<const char*> close(last + 1, nullptr);
+        run([&](size_t c) {
+            if (c > last) return;
+            bool s = in_str[c] != 0;
+            long long dep = dep0[c];
+            const char* e = cb(c + 1);
+            for (const char* q = next_structural(cb(c), e, true); q < e; q = next_structural(q + 1, e, true)) {
+                const char ch = *q;
+                if (ch == '"') { if (real_quote(q, rb)) s = !s; }
+                else if (!s) {
+                    if (ch == '{' || ch == '[') ++dep;
+                    else if (ch == ',') { if (dep == 1) commas[c].push_back(q); }
+                    else if (--dep == 0) { close[c] = q; return; }
+                }
+            }
+        });
+        const char* end_pos = nullptr;
+        size_t end_chunk = 0;
+        for (size_t c = 0; c <= last; ++c) if (close[c]) { end_pos = close[c]; end_chunk = c; break; }
+        if (!end_pos || *end_pos != ']') return false;
+        std::vector<std::pair<const char*, const char*>> elems;
+        const char* b = rb;
+        auto add = [&](const char* e) -> bool {
+            const char* x = b;
+            const char* y = e;
+            while (x < y && is_ws(*x)) ++x;
+            while (y > x && is_ws(*(y - 1))) --y;
+            if (x == y) return false;
+            elems.emplace_back(x, y);
+            return true;
+        };
+        for (size_t c = 0; c <= end_chunk; ++c)
+            for (const char* q : commas[c]) {
+                if (q > end_pos) break;
+                if (!add(q)) return false;
+                b = q + 1;
+            }
+        if (!add(end_pos)) return false;  // "[x, ]" is for the serial scan to reject
+        d->elements.insert(d->elements.end(), elems.begin(), elems.end());
+        p_ = end_pos + 1;
+        return true;
+    }
 
     // Skips one value without building it; the text must be well formed as far as brackets and strings go
     // (anything else is caught when the element itself is parsed).
@@ -186,11 +327,18 @@ private:
         for (DeferredArray& e : *deferred_) if (e.key == key) d = &e;
         if (!d) { deferred_->emplace_back(); d = &deferred_->back(); d->key = key; }
         d->elements.clear();
+        const char* const begin = p_;
         ++p_;  // '['
         skip_ws();
         if (p_ != end_ && *p_ == ']') { ++p_; return; }
+        bool tried = false;
         while (true) {
             skip_ws();
+            // an array that is still open after 1 MB is a big one: the rest is scanned by all threads
+            if (!tried && p_ - begin > (1 << 20) && (size_t)(end_ - p_) > ((size_t)4 << 20)) {
+                tried = true;
+                if (defer_rest_parallel(d)) return;
+            }
             const char* b = p_;
             skip_value();
             d->elements.emplace_back(b, p_);

@@ -512,6 +512,7 @@ void load_scene_json(const std::string& path, const std::string& texture_dir, Ho
     std::vector<jsonmin::DeferredArray> shape_arrays;
     jsonmin::Parser parser(text.data, text.data + text.size);
     parser.defer({"spheres", "cubes", "rectangles", "planes"}, &shape_arrays);
+    parser.set_threads(host_threads());
     Value root = parser.parse_document();
     const auto t2 = now();
     if (!root.is_object()) throw std::runtime_error("scene root must be a JSON object");

@@ -121,6 +121,11 @@ def test_parallel_loader_builds_the_scene_a_serial_loader_builds(rt, tmp_path):
     host thread and with many, and identical to the oracle's independent Python loader + C++ builder."""
     from ray_tracying_b200 import scenes
     sc = scenes.mixed_scene(30000, seed=5, resolution=(64, 36), texture_file="checker.jpg")
+    # strings with brackets, quotes and backslashes inside the big arrays: the multi-threaded bracket scan must see through them
+    weird = dict(sc["spheres"][7]["material"], texture_file='a]b[{"x\\.jpg')
+    for i in (3, 2000, 7000, 10400):
+        sc["spheres"][i] = dict(sc["spheres"][i], material=weird, note='}],[{ \\" ]')
+    sc["cubes"][5000] = dict(sc["cubes"][5000], note='\\\\"]')
     sc["planes"][100:100] = [{"corners": [[0, 0, 0]]}, 7, {"corners": "x"}]
     sc["spheres"][50:50] = [{"rotation": [0, 0, 0]}, {"location": [0, 0, 0], "material": {"diffuse_color": [1, 2]}}]
     sc["cubes"][10:10] = [{"rotation": [0, 0, 0]}]
