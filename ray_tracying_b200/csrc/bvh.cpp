@@ -51,17 +51,32 @@ void parallel_chunks(size_t n, size_t min_chunk, Fn fn) {
 }
 
 struct BuildCtx {
-    const std::vector<HostPrim>& prims;
+    std::vector<Box> box;          // the shapes' boxes, compact (24 B each: the builder touches them in sorted order)
     std::vector<int>& order;
     std::vector<float> centre[3];  // (lo+hi)/2 per axis, acceleration.cpp:49-50
 };
 
+// union of the boxes of order[start, end): min / max are exact, so any grouping gives the reference's union
 Box range_box(const BuildCtx& c, int start, int end) {
     Box b;
     for (int i = 0; i < 3; ++i) { b.lo[i] = FLT_MAX; b.hi[i] = -FLT_MAX; }
-    for (int k = start; k < end; ++k) {
-        const Box& pb = c.prims[c.order[k]].box;
-        for (int i = 0; i < 3; ++i) { b.lo[i] = std::min(b.lo[i], pb.lo[i]); b.hi[i] = std::max(b.hi[i], pb.hi[i]); }
+    auto scan = [&](size_t a0, size_t a1, Box& out) {
+        for (size_t k = (size_t)start + a0; k < (size_t)start + a1; ++k) {
+            const Box& pb = c.box[(size_t)c.order[k]];
+            for (int i = 0; i < 3; ++i) { out.lo[i] = std::min(out.lo[i], pb.lo[i]); out.hi[i] = std::max(out.hi[i], pb.hi[i]); }
+        }
+    };
+    if (end - start >= (1 << 17)) {
+        std::mutex mu;
+        parallel_chunks((size_t)(end - start), 1 << 15, [&](size_t a0, size_t a1) {
+            Box part;
+            for (int i = 0; i < 3; ++i) { part.lo[i] = FLT_MAX; part.hi[i] = -FLT_MAX; }
+            scan(a0, a1, part);
+            std::lock_guard<std::mutex> lock(mu);
+            for (int i = 0; i < 3; ++i) { b.lo[i] = std::min(b.lo[i], part.lo[i]); b.hi[i] = std::max(b.hi[i], part.hi[i]); }
+        });
+    } else {
+        scan(0, (size_t)(end - start), b);
     }
     return b;
 }
@@ -107,35 +122,50 @@ void sort_ranges(BuildCtx& c, int start, int end, int par_depth) {
 }
 
 // Pass 2: pre-order node array; boxes bottom-up (min/max are exact, so the union of the two
-// children equals the reference's union over the whole range).
-int emit_nodes(HostScene& s, int start, int end) {
-    const int me = (int)s.tree.size();
-    s.tree.emplace_back();
-    if (end - start <= 4) {
-        TreeNode& n = s.tree[me];
-        n.first = start;
-        n.count = end - start;
-        for (int i = 0; i < 3; ++i) { n.box.lo[i] = FLT_MAX; n.box.hi[i] = -FLT_MAX; }
-        for (int k = start; k < end; ++k) {
-            const Box& pb = s.prims[s.order[k]].box;
-            for (int i = 0; i < 3; ++i) { n.box.lo[i] = std::min(n.box.lo[i], pb.lo[i]); n.box.hi[i] = std::max(n.box.hi[i], pb.hi[i]); }
-        }
-        s.n_leaves++;
-        return me;
+// children equals the reference's union over the whole range). The split is always at floor(m / 2), so the
+// number of nodes below a range depends on its size only: sub-trees know their place in the array and
+// are written on different threads.
+struct NodeCount {
+    std::vector<std::pair<int, int>> memo;  // (range size, nodes): two sizes per level
+    int operator()(int m) {
+        if (m <= 4) return 1;
+        for (const auto& e : memo) if (e.first == m) return e.second;
+        const int v = 1 + (*this)(m / 2) + (*this)(m - m / 2);
+        memo.emplace_back(m, v);
+        return v;
     }
-    const int mid = (start + end) / 2;
-    const int l = emit_nodes(s, start, mid);
-    const int r = emit_nodes(s, mid, end);
-    TreeNode& n = s.tree[me];
-    n.left = l;
-    n.right = r;
+};
+
+void emit_nodes(HostScene& s, const std::vector<Box>& box, NodeCount& count, int start, int end, int me, int par_depth) {
+    TreeNode& n = s.tree[(size_t)me];
     n.first = start;
     n.count = end - start;
-    for (int i = 0; i < 3; ++i) {
-        n.box.lo[i] = std::min(s.tree[l].box.lo[i], s.tree[r].box.lo[i]);
-        n.box.hi[i] = std::max(s.tree[l].box.hi[i], s.tree[r].box.hi[i]);
+    if (end - start <= 4) {
+        n.left = n.right = -1;
+        for (int i = 0; i < 3; ++i) { n.box.lo[i] = FLT_MAX; n.box.hi[i] = -FLT_MAX; }
+        for (int k = start; k < end; ++k) {
+            const Box& pb = box[(size_t)s.order[(size_t)k]];
+            for (int i = 0; i < 3; ++i) { n.box.lo[i] = std::min(n.box.lo[i], pb.lo[i]); n.box.hi[i] = std::max(n.box.hi[i], pb.hi[i]); }
+        }
+        return;
     }
-    return me;
+    const int mid = (start + end) / 2;
+    const int l = me + 1, r = me + 1 + count(mid - start);
+    if (par_depth > 0 && end - start > (1 << 14)) {
+        NodeCount other = count;  // the memo is not shared between threads
+        auto fut = std::async(std::launch::async, [&s, &box, other, start, mid, l, par_depth]() mutable { emit_nodes(s, box, other, start, mid, l, par_depth - 1); });
+        emit_nodes(s, box, count, mid, end, r, par_depth - 1);
+        fut.get();
+    } else {
+        emit_nodes(s, box, count, start, mid, l, 0);
+        emit_nodes(s, box, count, mid, end, r, 0);
+    }
+    n.left = l;
+    n.right = r;
+    for (int i = 0; i < 3; ++i) {
+        n.box.lo[i] = std::min(s.tree[(size_t)l].box.lo[i], s.tree[(size_t)r].box.lo[i]);
+        n.box.hi[i] = std::max(s.tree[(size_t)l].box.hi[i], s.tree[(size_t)r].box.hi[i]);
+    }
 }
 
 inline float bits_f(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
@@ -151,15 +181,27 @@ void build_bvh(HostScene& s) {
     s.tree.clear();
     s.n_leaves = 0;
     if (n == 0) return;
-    BuildCtx c{s.prims, s.order, {}};
-    for (int a = 0; a < 3; ++a) {
-        c.centre[a].resize(n);
-        for (int i = 0; i < n; ++i) c.centre[a][i] = (s.prims[i].box.lo[a] + s.prims[i].box.hi[a]) / 2.0f;
-    }
+    BuildCtx c{{}, s.order, {}};
+    c.box.resize((size_t)n);
+    for (int a = 0; a < 3; ++a) c.centre[a].resize((size_t)n);
+    parallel_chunks((size_t)n, 1 << 15, [&](size_t i0, size_t i1) {
+        for (size_t i = i0; i < i1; ++i) {
+            c.box[i] = s.prims[i].box;
+            for (int a = 0; a < 3; ++a) c.centre[a][i] = (s.prims[i].box.lo[a] + s.prims[i].box.hi[a]) / 2.0f;
+        }
+    });
+    const auto t1 = std::chrono::steady_clock::now();
     sort_ranges(c, 0, n, 6);  // up to 64 sub-trees in flight
-    s.tree.reserve((size_t)n);
-    emit_nodes(s, 0, n);
-    s.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const auto t2 = std::chrono::steady_clock::now();
+    NodeCount count;
+    s.tree.assign((size_t)count(n), TreeNode{});
+    emit_nodes(s, c.box, count, 0, n, 0, 6);
+    for (const TreeNode& t : s.tree) if (t.left < 0) s.n_leaves++;
+    const auto t3 = std::chrono::steady_clock::now();
+    s.build_seconds = std::chrono::duration<double>(t3 - t0).count();
+    if (std::getenv("RT_B200_DEBUG"))
+        std::fprintf(stderr, "[rt_b200] reference BVH: centres %.3f s, sorts %.3f s, nodes %.3f s\n", std::chrono::duration<double>(t1 - t0).count(),
+                     std::chrono::duration<double>(t2 - t1).count(), std::chrono::duration<double>(t3 - t2).count());
 }
 
 namespace {
@@ -350,12 +392,25 @@ struct SahBuilder {
             axis_ok[a] = ext > 0.0f && ext < 1e30f;
             scale3[a] = axis_ok[a] ? (float)NB / ext : 0.0f;
         }
-        // pass 2: the items into 16 bins per axis
-        std::unique_ptr<Bins> total(new Bins());
+        // pass 2: the items into 16 bins per axis (on the stack: the recursion is ~40 deep, 2.6 KB per level)
+        Bins total_store;
+        Bins* const total = &total_store;
         for (int a = 0; a < 3; ++a) for (int b = 0; b < NB; ++b) { box_reset(total->bins[a][b]); total->cnt[a][b] = 0; }
         {
             std::mutex mu;
             auto scan = [&](size_t a0, size_t b0) {
+                if (!wide_scan) {  // the only scanner: straight into the totals
+                    for (size_t k = (size_t)lo + a0; k < (size_t)lo + b0; ++k) {
+                        const Box& bx = items[k].box;
+                        for (int a = 0; a < 3; ++a) {
+                            if (!axis_ok[a]) continue;
+                            const int bi = bin_of(bx, a, cb.lo[a], scale3[a]);
+                            box_merge(total->bins[a][bi], bx);
+                            total->cnt[a][bi]++;
+                        }
+                    }
+                    return;
+                }
                 std::unique_ptr<Bins> loc(new Bins());
                 for (int a = 0; a < 3; ++a) for (int b = 0; b < NB; ++b) { box_reset(loc->bins[a][b]); loc->cnt[a][b] = 0; }
                 for (size_t k = (size_t)lo + a0; k < (size_t)lo + b0; ++k) {
@@ -471,48 +526,66 @@ void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root, const
     struct Plan { int up, level, sp, first; int slots[4]; int8_t n, ni; };
     std::vector<float> area(up.size());
     parallel_chunks(up.size(), 1 << 16, [&](size_t a, size_t b) { for (size_t i = a; i < b; ++i) area[i] = (float)half_area(up[i].box); });
+    // breadth-first, one level at a time: the nodes of a level pick their children in parallel, a prefix sum over the
+    // level numbers the children (node index == position in `plan`)
     std::vector<Plan> plan;
     plan.reserve(up.size() / 2 + 2);
     plan.push_back({root, 1, 0, 0, {0, 0, 0, 0}, 0, 0});
     s.stack_need = 1;
     s.wide_depth = 0;
-    size_t n_nodes = 1;
-    for (size_t qi = 0; qi < plan.size(); ++qi) {
-        Plan it = plan[qi];
-        s.wide_depth = std::max(s.wide_depth, it.level);
-        const UpNode& u = up[(size_t)it.up];
-        int* slots = it.slots;
-        int n = 0;
-        if (u.left < 0) slots[n++] = it.up;  // a scene of one primitive: the root holds it
-        else {
-            slots[n++] = u.left;
-            slots[n++] = u.right;
+    size_t level_begin = 0;
+    while (level_begin < plan.size()) {
+        const size_t level_end = plan.size();
+        s.wide_depth = std::max(s.wide_depth, plan[level_begin].level);
+        parallel_chunks(level_end - level_begin, 1 << 12, [&](size_t a, size_t b) {
+            for (size_t qi = level_begin + a; qi < level_begin + b; ++qi) {
+                Plan& it = plan[qi];
+                const UpNode& u = up[(size_t)it.up];
+                int* slots = it.slots;
+                int n = 0;
+                if (u.left < 0) slots[n++] = it.up;  // a scene of one primitive: the root holds it
+                else {
+                    slots[n++] = u.left;
+                    slots[n++] = u.right;
+                }
+                while (n < 4) {  // open the inner child with the largest surface area
+                    int pick = -1;
+                    float best = -1.0f;
+                    for (int k = 0; k < n; ++k)
+                        if (up[(size_t)slots[k]].left >= 0 && area[(size_t)slots[k]] > best) { best = area[(size_t)slots[k]]; pick = k; }
+                    if (pick < 0) break;
+                    const int c = slots[pick];
+                    slots[pick] = up[(size_t)c].left;
+                    slots[n++] = up[(size_t)c].right;
+                }
+                // inner children first (consecutive node indices), primitives behind them
+                std::stable_partition(slots, slots + n, [&](int c) { return up[(size_t)c].left >= 0; });
+                int ni = 0;
+                while (ni < n && up[(size_t)slots[ni]].left >= 0) ++ni;
+                it.n = (int8_t)n;
+                it.ni = (int8_t)ni;
+            }
+        });
+        size_t next = level_end;
+        for (size_t qi = level_begin; qi < level_end; ++qi) {
+            Plan& it = plan[qi];
+            it.first = (int)next;
+            next += (size_t)it.ni;
+            // the traversal pushes up to ni - 1 sibling nodes before it descends: the stack a ray can need below here
+            s.stack_need = std::max(s.stack_need, it.sp + std::max(0, (int)it.ni - 1) + 1);
         }
-        while (n < 4) {  // open the inner child with the largest surface area
-            int pick = -1;
-            float best = -1.0f;
-            for (int k = 0; k < n; ++k)
-                if (up[(size_t)slots[k]].left >= 0 && area[(size_t)slots[k]] > best) { best = area[(size_t)slots[k]]; pick = k; }
-            if (pick < 0) break;
-            const int c = slots[pick];
-            slots[pick] = up[(size_t)c].left;
-            slots[n++] = up[(size_t)c].right;
-        }
-        // inner children first (consecutive node indices), primitives behind them
-        std::stable_partition(slots, slots + n, [&](int c) { return up[(size_t)c].left >= 0; });
-        int ni = 0;
-        while (ni < n && up[(size_t)slots[ni]].left >= 0) ++ni;
-        if (n_nodes + (size_t)ni >= (1u << 30)) throw std::runtime_error("too many BVH nodes");
-        it.first = (int)n_nodes;
-        it.n = (int8_t)n;
-        it.ni = (int8_t)ni;
-        plan[qi] = it;
-        // the traversal pushes up to ni - 1 sibling nodes before it descends: the stack a ray can need below here
-        const int pushed = std::max(0, ni - 1);
-        s.stack_need = std::max(s.stack_need, it.sp + pushed + 1);
-        for (int k = 0; k < ni; ++k) plan.push_back({slots[k], it.level + 1, it.sp + pushed, 0, {0, 0, 0, 0}, 0, 0});
-        n_nodes += (size_t)ni;
+        if (next >= (1u << 30)) throw std::runtime_error("too many BVH nodes");
+        plan.resize(next);
+        parallel_chunks(level_end - level_begin, 1 << 12, [&](size_t a, size_t b) {
+            for (size_t qi = level_begin + a; qi < level_begin + b; ++qi) {
+                const Plan it = plan[qi];
+                const int pushed = std::max(0, (int)it.ni - 1);
+                for (int k = 0; k < it.ni; ++k) plan[(size_t)it.first + (size_t)k] = {it.slots[k], it.level + 1, it.sp + pushed, 0, {0, 0, 0, 0}, 0, 0};
+            }
+        });
+        level_begin = level_end;
     }
+    const size_t n_nodes = plan.size();
     s.dwide.assign(n_nodes, empty_wide());
     parallel_chunks(plan.size(), 1 << 14, [&](size_t a, size_t b) {
         for (size_t qi = a; qi < b; ++qi) {
@@ -645,7 +718,8 @@ void flatten_scene(HostScene& s) {
             b.items.resize((size_t)n);
             for (int k = 0; k < n; ++k) b.items[(size_t)k] = {abox[(size_t)k], k};
             b.nodes.resize(2 * (size_t)n);
-            const int root = b.build(0, n, 6);
+            static const int sah_par = [] { const char* e = std::getenv("RT_B200_SAH_PAR"); return e ? std::atoi(e) : 8; }();  // sub-trees built on other threads down to this depth
+            const int root = b.build(0, n, sah_par);
             lap("SAH build");
             emit_wide_tree(s, b.nodes, root, cull, cq);
             lap("collapse + emit");
