@@ -526,6 +526,7 @@ void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root, const
     struct Plan { int up, level, sp, first; int slots[4]; int8_t n, ni; };
     std::vector<float> area(up.size());
     parallel_chunks(up.size(), 1 << 16, [&](size_t a, size_t b) { for (size_t i = a; i < b; ++i) area[i] = (float)half_area(up[i].box); });
+    const int child_order = [] { const char* e = std::getenv("RT_B200_CHILD_ORDER"); return !e ? 0 : (std::string(e) == "area" ? 1 : (std::string(e) == "small" ? -1 : 0)); }();
     // breadth-first, one level at a time: the nodes of a level pick their children in parallel, a prefix sum over the
     // level numbers the children (node index == position in `plan`)
     std::vector<Plan> plan;
@@ -562,6 +563,12 @@ void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root, const
                 std::stable_partition(slots, slots + n, [&](int c) { return up[(size_t)c].left >= 0; });
                 int ni = 0;
                 while (ni < n && up[(size_t)slots[ni]].left >= 0) ++ni;
+                // slot order is the visit order of the any-hit packets (the other loops sort by entry distance):
+                // RT_B200_CHILD_ORDER=area puts the largest boxes first, =small the smallest
+                if (child_order != 0) {
+                    std::stable_sort(slots, slots + ni, [&](int x, int y) { return child_order > 0 ? area[(size_t)x] > area[(size_t)y] : area[(size_t)x] < area[(size_t)y]; });
+                    std::stable_sort(slots + ni, slots + n, [&](int x, int y) { return child_order > 0 ? area[(size_t)x] > area[(size_t)y] : area[(size_t)x] < area[(size_t)y]; });
+                }
                 it.n = (int8_t)n;
                 it.ni = (int8_t)ni;
             }
