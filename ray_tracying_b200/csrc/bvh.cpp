@@ -526,7 +526,13 @@ void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root, const
     struct Plan { int up, level, sp, first; int slots[4]; int8_t n, ni; };
     std::vector<float> area(up.size());
     parallel_chunks(up.size(), 1 << 16, [&](size_t a, size_t b) { for (size_t i = a; i < b; ++i) area[i] = (float)half_area(up[i].box); });
-    const int child_order = [] { const char* e = std::getenv("RT_B200_CHILD_ORDER"); return !e ? 0 : (std::string(e) == "area" ? 1 : (std::string(e) == "small" ? -1 : 0)); }();
+    const int child_order = [] {
+        const char* e = std::getenv("RT_B200_CHILD_ORDER");
+        const std::string v = e ? e : "";
+        return v == "area" ? 1 : (v == "small" ? -1 : (v == "low" ? 2 : (v == "light_near" ? 3 : (v == "light_far" ? 4 : 0))));
+    }();
+    float light0[3] = {0, 0, 0};
+    if (!s.lights.empty()) for (int a = 0; a < 3; ++a) light0[a] = s.lights[0].location[a];
     // breadth-first, one level at a time: the nodes of a level pick their children in parallel, a prefix sum over the
     // level numbers the children (node index == position in `plan`)
     std::vector<Plan> plan;
@@ -566,8 +572,17 @@ void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root, const
                 // slot order is the visit order of the any-hit packets (the other loops sort by entry distance):
                 // RT_B200_CHILD_ORDER=area puts the largest boxes first, =small the smallest
                 if (child_order != 0) {
-                    std::stable_sort(slots, slots + ni, [&](int x, int y) { return child_order > 0 ? area[(size_t)x] > area[(size_t)y] : area[(size_t)x] < area[(size_t)y]; });
-                    std::stable_sort(slots + ni, slots + n, [&](int x, int y) { return child_order > 0 ? area[(size_t)x] > area[(size_t)y] : area[(size_t)x] < area[(size_t)y]; });
+                    auto key = [&](int x) -> float {
+                        const Box& b = up[(size_t)x].box;
+                        if (child_order == 1) return -area[(size_t)x];
+                        if (child_order == -1) return area[(size_t)x];
+                        if (child_order == 2) return b.lo[2] + b.hi[2];  // lowest first
+                        float d2 = 0.0f;                                   // distance of the box centre from the first light
+                        for (int a = 0; a < 3; ++a) { const float c = 0.5f * (b.lo[a] + b.hi[a]) - light0[a]; d2 += c * c; }
+                        return child_order == 3 ? d2 : -d2;               // 3: nearest to the light first, 4: farthest first
+                    };
+                    std::stable_sort(slots, slots + ni, [&](int x, int y) { return key(x) < key(y); });
+                    std::stable_sort(slots + ni, slots + n, [&](int x, int y) { return key(x) < key(y); });
                 }
                 it.n = (int8_t)n;
                 it.ni = (int8_t)ni;
