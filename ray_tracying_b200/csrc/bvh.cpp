@@ -526,22 +526,23 @@ void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root, const
     struct Plan { int up, level, sp, first; int slots[4]; int8_t n, ni; };
     std::vector<float> area(up.size());
     parallel_chunks(up.size(), 1 << 16, [&](size_t a, size_t b) { for (size_t i = a; i < b; ++i) area[i] = (float)half_area(up[i].box); });
-    // Visit order of the any-hit PACKETS (every other loop sorts the children by entry distance). Shadow rays all end
-    // at the light, so "farthest from the light first" is near-first for them at no run-time cost: the node carries,
-    // for the first two lights, the rank of every child in that order (meta bits 8-15 and 24-31, 2 bits per slot) and
-    // the packet loop sorts by the rank of the light its rays go to. Measured on configs[2] (one area light) with the
-    // order baked into the slots: 378 -> 363 ms for the shadow kernel, against 439 / 496 ms for lowest-first /
-    // nearest-to-the-light-first and 434 / 445 ms for largest / smallest box first (profiles/ab_r2l*.jsonl).
-    // RT_B200_CHILD_ORDER = area | small | low | light_near | light_far re-orders the SLOTS instead (A/B).
+    // Slot order = visit order of the any-hit PACKETS (every other loop sorts the children by entry distance).
+    // Shadow rays all end at the light, so "farthest from the light first" is near-first for them at no run-time
+    // cost: measured on configs[2] (one area light) 378 -> 363 ms for the shadow kernel, against 439 / 496 ms for
+    // lowest-first / nearest-to-the-light-first and 434 / 445 ms for largest / smallest box first
+    // (profiles/ab_r2l*.jsonl). With several lights one static order cannot suit them all (measured neutral for two
+    // opposite lights): the construction order is kept. (Per-light ranks in the node, chosen per packet at run time,
+    // were measured too: the sort they need in the packet loop costs 8 %, twice what the better order gives:
+    // profiles/ab_r2m_ab.jsonl.) RT_B200_CHILD_ORDER = default | area | small | low |
+    // light_near | light_far overrides.
     const int child_order = [&] {
         const char* e = std::getenv("RT_B200_CHILD_ORDER");
         const std::string v = e ? e : "";
+        if (v.empty()) return s.lights.size() == 1 ? 4 : 0;
         return v == "area" ? 1 : (v == "small" ? -1 : (v == "low" ? 2 : (v == "light_near" ? 3 : (v == "light_far" ? 4 : 0))));
     }();
-    float light0[3] = {0, 0, 0}, light1[3] = {0, 0, 0};
-    if (!s.lights.empty()) for (int a = 0; a < 3; ++a) light0[a] = light1[a] = s.lights[0].location[a];
-    if (s.lights.size() > 1) for (int a = 0; a < 3; ++a) light1[a] = s.lights[1].location[a];
-    const bool light_ranks = !s.lights.empty() && std::getenv("RT_B200_NO_LIGHT_ORDER") == nullptr;
+    float light0[3] = {0, 0, 0};
+    if (!s.lights.empty()) for (int a = 0; a < 3; ++a) light0[a] = s.lights[0].location[a];
     // breadth-first, one level at a time: the nodes of a level pick their children in parallel, a prefix sum over the
     // level numbers the children (node index == position in `plan`)
     std::vector<Plan> plan;
@@ -636,24 +637,6 @@ void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root, const
                     qmax = std::max(qmax, cq[(size_t)c.prim]);
                 } else {
                     set_child_box(w, k, c.box);
-                }
-            }
-            // rank of every child in "farthest from the light first" order, for the first two lights; without lights
-            // (or with RT_B200_NO_LIGHT_ORDER) the rank is the slot
-            for (int li = 0; li < 2; ++li) {
-                const float* L = li == 0 ? light0 : light1;
-                float d2[4] = {0, 0, 0, 0};
-                for (int k = 0; k < it.n; ++k) {
-                    const Box& b = up[(size_t)it.slots[k]].box;
-                    for (int a = 0; a < 3; ++a) { const float c = 0.5f * (b.lo[a] + b.hi[a]) - L[a]; d2[k] += c * c; }
-                }
-                for (int k = 0; k < 4; ++k) {
-                    uint32_t rank = (uint32_t)k;
-                    if (light_ranks && k < it.n) {
-                        rank = 0;
-                        for (int j = 0; j < it.n; ++j) if (d2[j] > d2[k] || (d2[j] == d2[k] && j < k)) ++rank;
-                    }
-                    meta |= rank << ((li == 0 ? 8 : 24) + 2 * k);
                 }
             }
             w.f[24] = bits_f((uint32_t)it.first);

@@ -36,8 +36,7 @@ struct alignas(128) DPrim { F4 q[8]; };
 //   f[24] = bits: node index of child 0 -- the INNER children of a node occupy slots 0..ni-1 and are
 //           consecutive nodes (first + slot); primitive children follow in slots ni..n-1
 //   f[25] = bits: meta = valid mask (bits 0-3) | primitive mask (bits 4-7: the child is a primitive) |
-//           primitive types, 2 bits per child (bits 16-23) | visit rank of every child for shadow rays to light 0
-//           (bits 8-15, 2 bits per child: farthest from the light first) and to light 1 (bits 24-31)
+//           primitive types, 2 bits per child (bits 16-23)
 //   f[26] = Q: quadratic cull coefficient (largest over the spheres BELOW this node, else 0)
 //   f[27..30] = bits: sorted position of the primitive in slot 0..3 (primitive children only)
 //   f[31] unused
