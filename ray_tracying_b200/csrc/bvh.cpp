@@ -538,25 +538,11 @@ void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root, const
     const int child_order = [&] {
         const char* e = std::getenv("RT_B200_CHILD_ORDER");
         const std::string v = e ? e : "";
-        if (v.empty()) return s.lights.size() == 1 ? 4 : (s.lights.size() >= 2 ? 5 : 0);
+        if (v.empty()) return s.lights.size() == 1 ? 4 : 0;
         return v == "area" ? 1 : (v == "small" ? -1 : (v == "low" ? 2 : (v == "light_near" ? 3 : (v == "light_far" ? 4 : 0))));
     }();
-    float light0[3] = {0, 0, 0}, light_axis[3] = {0, 0, 0};
+    float light0[3] = {0, 0, 0};
     if (!s.lights.empty()) for (int a = 0; a < 3; ++a) light0[a] = s.lights[0].location[a];
-    // Several lights: one static order cannot be near-first for all of them, but an order and its REVERSE can serve
-    // two sides: the children are sorted along the axis light 0 -> light 1 (farthest from light 0 first), shadow rays
-    // to light 0 take the slots forwards, rays to a light on the other side backwards (HostScene::light_reverse_mask,
-    // one bit per light; the packet loop flips the keys with one XOR per child).
-    s.light_reverse_mask = 0u;
-    if (child_order == 5) {
-        float mid[3];
-        for (int a = 0; a < 3; ++a) { light_axis[a] = s.lights[1].location[a] - s.lights[0].location[a]; mid[a] = 0.5f * (s.lights[1].location[a] + s.lights[0].location[a]); }
-        for (size_t li = 0; li < s.lights.size() && li < 32; ++li) {
-            float d = 0.0f;
-            for (int a = 0; a < 3; ++a) d += (s.lights[li].location[a] - mid[a]) * light_axis[a];
-            if (d > 0.0f) s.light_reverse_mask |= 1u << li;
-        }
-    }
     // breadth-first, one level at a time: the nodes of a level pick their children in parallel, a prefix sum over the
     // level numbers the children (node index == position in `plan`)
     std::vector<Plan> plan;
@@ -601,11 +587,6 @@ void emit_wide_tree(HostScene& s, const std::vector<UpNode>& up, int root, const
                         if (child_order == 1) return -area[(size_t)x];
                         if (child_order == -1) return area[(size_t)x];
                         if (child_order == 2) return b.lo[2] + b.hi[2];  // lowest first
-                        if (child_order == 5) {  // along the axis light 0 -> light 1: farthest from light 0 first
-                            float d = 0.0f;
-                            for (int a = 0; a < 3; ++a) d += (0.5f * (b.lo[a] + b.hi[a]) - light0[a]) * light_axis[a];
-                            return -d;
-                        }
                         float d2 = 0.0f;                                   // distance of the box centre from the first light
                         for (int a = 0; a < 3; ++a) { const float c = 0.5f * (b.lo[a] + b.hi[a]) - light0[a]; d2 += c * c; }
                         return child_order == 3 ? d2 : -d2;               // 3: nearest to the light first, 4: farthest first

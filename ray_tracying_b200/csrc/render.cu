@@ -429,8 +429,6 @@ RT_DEV void packet_loop(const BvhView& bvh, Src& src, unsigned int* counter, uns
             else if (trav_begin<ANY>(bvh, s, r, max_t)) { src.store(item, s); active = false; }
         }
         const bool traversing = active;
-        // any-hit packets take the children in slot order, or backwards for a light on the other side (bvh.cpp)
-        const int flip = (ANY && ((bvh.light_reverse_mask >> (__shfl_sync(FULL, src.order_hint(), 0) & 31)) & 1u)) ? 3 : 0;
         unsigned int alive = __ballot_sync(FULL, active);  // lanes still looking for an answer
         unsigned int sp = stk0;
         int cur = 0;
@@ -495,7 +493,7 @@ RT_DEV void packet_loop(const BvhView& bvh, Src& src, unsigned int* counter, uns
                     const unsigned int bk = k == 0 ? b0 : (k == 1 ? b1 : (k == 2 ? b2 : b3));
                     int v = 0x7fffffff;
                     if (bk != 0u) {
-                        if (ANY && !RT_ANY_SORTED_PACKET) v = ((k ^ flip) << 2) | k;  // slot order, forwards or backwards
+                        if (ANY && !RT_ANY_SORTED_PACKET) v = k;  // slot order
                         else {
                             const int mine = (((pm >> k) & 1u) != 0u) ? __float_as_int(fmaxf(ent[k], 0.0f)) : 0x7fffffff;
                             v = (__reduce_min_sync(FULL, mine) & ~3) | k;
@@ -589,7 +587,6 @@ struct ViewRays {
         return !(b.x == 0.0f && b.y == 0.0f && b.z == 0.0f);
     }
     RT_DEV void store(long long item, const TravState& s) const { hit_prim[item] = s.best_prim; }
-    RT_DEV int order_hint() const { return 0; }
 };
 
 template <bool STATS>
@@ -838,7 +835,6 @@ struct ShadowRaysT {
     int* vis;
     unsigned int n_recs;
     int* vis_slot;
-    int light;  // light of the item loaded last (order_hint)
     // false: the record is invalid (level 0: the view ray missed)
     RT_DEV bool load(long long item, Ray& sr, float& max_t) {
         unsigned long long rest = (unsigned long long)item;
@@ -853,7 +849,6 @@ struct ShadowRaysT {
             rest -= block;
             ++li;
         }
-        light = li;
         const unsigned int rec = (unsigned int)(rest / (unsigned int)cnt);
         const int k = (int)(rest % (unsigned int)cnt);
         const float4 r0 = ld_once_rw(recs + (size_t)rec * 5 + 0);
@@ -888,7 +883,6 @@ struct ShadowRaysT {
     }
     // nothing closer than the light: this sample is lit (raytracer.cpp:233-235)
     RT_DEV void store(long long, const TravState& s) const { if (s.best_prim < 0) atomicAdd(vis_slot, 1); }
-    RT_DEV int order_hint() const { return light; }  // the light these rays go to
 };
 typedef ShadowRaysT<false> ShadowRays;
 typedef ShadowRaysT<RT_SELF_OCCLUSION != 0> ShadowRaysPacket;
@@ -898,7 +892,7 @@ __global__ void __launch_bounds__(RT_TRACE_THREADS, RT_WAVE_MINBLOCKS) shadow_ke
     unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
     const unsigned long long n = (unsigned long long)lv[L_RECS] * (unsigned long long)p.shadow_per_rec;
     TraceStats st = {0u, 0u};
-    ShadowRays src = {p, p.recs[level & 1], p.vis[level & 1], lv[L_RECS], nullptr, 0};
+    ShadowRays src = {p, p.recs[level & 1], p.vis[level & 1], lv[L_RECS], nullptr};
     wave_loop<true, STATS>(p.bvh, src, lv + L_WORK_SHADOW, n, st);
     if (STATS) flush_stats(p, st);
 }
@@ -908,7 +902,7 @@ __global__ void __launch_bounds__(RT_TRACE_THREADS, RT_TRACE_MINBLOCKS) shadow_p
     unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
     const unsigned long long n = (unsigned long long)lv[L_RECS] * (unsigned long long)p.shadow_per_rec;
     TraceStats st = {0u, 0u};
-    ShadowRaysPacket src = {p, p.recs[level & 1], p.vis[level & 1], lv[L_RECS], nullptr, 0};
+    ShadowRaysPacket src = {p, p.recs[level & 1], p.vis[level & 1], lv[L_RECS], nullptr};
     packet_loop<true, STATS>(p.bvh, src, lv + L_WORK_SHADOW, n, st);
     if (STATS) flush_stats(p, st);
 }
@@ -918,7 +912,7 @@ __global__ void __launch_bounds__(128) shadow_literal_kernel(const __grid_consta
     unsigned int* lv = p.lvl + level * RT_LVL_STRIDE;
     const unsigned long long n = (unsigned long long)lv[L_RECS] * (unsigned long long)p.shadow_per_rec;
     TraceStats st = {0u, 0u};
-    ShadowRays src = {p, p.recs[level & 1], p.vis[level & 1], lv[L_RECS], nullptr, 0};
+    ShadowRays src = {p, p.recs[level & 1], p.vis[level & 1], lv[L_RECS], nullptr};
     literal_loop<true, STATS>(p.bvh, src, n, st);
     if (STATS) flush_stats(p, st);
 }
@@ -1438,7 +1432,6 @@ static int fill_params(const HostScene& h, const rt_render_params& rp, FramePara
     if (rp.reserved[5] < 0 || rp.reserved[5] > 1024) { set_error("tile block must be in [0,1024]"); return RT_ERR_INVALID; }
     std::memset(&k, 0, sizeof(k));
     k.bvh.n_prims = (int)h.dprims.size();
-    k.bvh.light_reverse_mask = h.light_reverse_mask;
     k.bvh.use_bvh = rp.use_bvh ? 1 : 0;
     k.bvh.prune = (rp.reserved[0] & 1) ? 0 : 1;  // reserved[0] bit 0: literal reference traversal (test hook)
     k.n_lights = (int)h.dlights.size();

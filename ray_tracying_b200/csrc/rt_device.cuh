@@ -315,7 +315,6 @@ struct BvhView {
     int prune;        // 0: visit everything, exact tests only (the reference's literal traversal)
     int stack_depth;  // entries per thread of the shared-memory traversal stack (per-ray kernels)
     int packet_stack_depth;  // entries per warp (packet kernels)
-    unsigned int light_reverse_mask;  // bit li: any-hit packets of light li visit a node's children in reverse slot order
     int n_staged;  // RT_STAGE_TOP builds: the first n_staged nodes (breadth-first = the top levels) are also in shared memory
 };
 

@@ -109,7 +109,6 @@ struct HostScene {
     std::vector<DWide> dwide;     // dwide[0] = root (empty when there are no shapes)
     std::vector<F4> dleafbox;     // per sorted primitive: (lo.xyz, 0), (hi.xyz, 0) of the EXACT box of its reference leaf
     int wide_depth = 0;           // levels of the wide tree
-    uint32_t light_reverse_mask = 0;  // bit li: the any-hit packets of light li take a node's children in reverse slot order
     int stack_need = 1;           // traversal stack entries a ray can need (max over root->leaf paths of the pushed siblings) + 1
     std::vector<DMaterial> dmaterials;
     std::vector<DLight> dlights;
