@@ -212,6 +212,7 @@ class Ranks:
         torch.cuda.set_device(self.local_rank)
         self.host_group = None
         if self.world > 1:
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version / debug lines must not share stdout with the JSON line
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
             # a HOST barrier (gloo): ranks that wait for rank 0's rt_render_multi must not spin on their GPUs
             self.host_group = dist.new_group(backend="gloo")
