@@ -212,8 +212,19 @@ class Ranks:
         torch.cuda.set_device(self.local_rank)
         self.host_group = None
         if self.world > 1:
-            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version / debug lines must not share stdout with the JSON line
-            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            # NCCL prints its version banner on stdout when the communicator is created: stdout carries the JSON line
+            # and nothing else, so fd 1 points at stderr until the first collective is through
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+                dist.barrier()
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
             # a HOST barrier (gloo): ranks that wait for rank 0's rt_render_multi must not spin on their GPUs
             self.host_group = dist.new_group(backend="gloo")
 
