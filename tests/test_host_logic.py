@@ -192,6 +192,27 @@ def test_shard_pixels_partition_the_frame(rt):
             assert counts == [int((owner == r).sum()) for r in range(world)]
 
 
+def test_shard_pixels_with_tile_blocks_and_a_window(rt):
+    """Tile blocks (B x B groups of tiles per owner) and the render window: the ranks still partition exactly the
+    pixels that are rendered, and rt_shard_pixels agrees with dist.tile_owner."""
+    scene = rt.Scene.from_json(os.path.join(GOLDEN, "mixed_400.json"), GOLDEN)
+    w, h = scene.resolution
+    from ray_tracying_b200 import dist
+    for world, tile, block in ((4, (8, 4), 3), (3, (16, 8), 2), (8, (32, 32), 4)):
+        owner = dist.tile_owner(w, h, tile, world, block)
+        counts = [scene.shard_pixels(rt.make_params(rank=r, world=world, tile=tile, tile_block=block)) for r in range(world)]
+        assert counts == [int((owner == r).sum()) for r in range(world)] and sum(counts) == w * h
+        win = (13, 7, w - 21, h - 30)
+        inside = np.zeros((h, w), dtype=bool)
+        inside[win[1]:win[3], win[0]:win[2]] = True
+        counts = [scene.shard_pixels(rt.make_params(rank=r, world=world, tile=tile, tile_block=block, window=win)) for r in range(world)]
+        assert counts == [int(((owner == r) & inside).sum()) for r in range(world)]
+    with pytest.raises(rt.RtError):
+        scene.shard_pixels(rt.make_params(window=(w + 5, 0, w + 9, 4)))  # empty after clipping to the frame
+    with pytest.raises(ValueError):
+        rt.make_params(window=(5, 5, 5, 9))
+
+
 def test_bad_params_are_rejected(rt):
     scene = rt.Scene.from_json(os.path.join(GOLDEN, "few_3.json"), GOLDEN)
     for kw in (dict(rank=2, world=2), dict(tile=(30, 32)), dict(tile=(32, 6))):
