@@ -485,7 +485,27 @@ RT_DEV void packet_loop(const BvhView& bvh, Src& src, unsigned int* counter, uns
                 if (primmask & 4u) b2 = 0u;
                 if (primmask & 8u) b3 = 0u;
             }
-            if (((b0 | b1 | b2 | b3) & alive) != 0u) {
+            if (ANY && !RT_ANY_SORTED_PACKET) {
+                // occlusion packets take the inner children in SLOT order (bvh.cpp chooses it at build time): no keys, no
+                // sorting network -- the first child with lanes is visited next, the others are pushed so that they
+                // pop in slot order
+                if (((b0 | b1 | b2 | b3) & alive) != 0u) {
+                    const int fs = b0 != 0u ? 0 : (b1 != 0u ? 1 : (b2 != 0u ? 2 : 3));  // warp-uniform
+#pragma unroll
+                    for (int k = 3; k >= 1; --k) {
+                        const unsigned int bk = k == 1 ? b1 : (k == 2 ? b2 : b3);
+                        if (bk != 0u && k != fs) {
+                            if (lane == 0)
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %3};" :: "r"(sp), "r"(first + k), "r"(bk), "r"(0) : "memory");
+                            sp += 16u;
+                            if (RT_CHECKS && sp > stk0 + (unsigned int)bvh.packet_stack_depth * 16u) __trap();
+                        }
+                    }
+                    cur = first + fs;
+                    curmask = (fs == 0 ? b0 : (fs == 1 ? b1 : (fs == 2 ? b2 : b3))) & alive;
+                    descended = curmask != 0u;
+                }
+            } else if (((b0 | b1 | b2 | b3) & alive) != 0u) {
                 // inner children, ordered by the packet's smallest entry parameter
                 int key[4];
 #pragma unroll
